@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- SoftPool + Chamfer fwd+bwd throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload A|A1|N8192]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One STEP = one pass of the hot path over one batch of B synthetic clouds (per GPU):
+  sp_topk_f32 -> sp_gather_fwd_f32 -> sp_gather_bwd_f32          (SoftPool fwd+bwd, keys given)
+  chamfer_fwd_f32 -> chamfer_loss_f32 -> chamfer_bwd_f32          (Chamfer fwd+bwd, n = m = N)
+`value` = whole-job Mpoints/s = (n_gpus * B * N points) / (max-over-ranks step time), inputs
+resident in HBM, the step replayed as a CUDA graph, inputs rotating over several buffer sets whose
+footprint exceeds the 126 MB L2.  `e2e` = same step through the public Python API with HOST
+(pinned) inputs, H2D/D2H copies inside the timed region.  `roofline` = dominant kernel, timed live
+with CUDA events in an instrumented pass (L2 flushed before every step).  `cpu_baseline` = the CPU
+port of the reference path (oracle/softpool_torch_port.py + oracle/chamfer_oracle.c) on this host.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: B (per GPU), C, N, R, k, cab -- Chamfer is n = m = N on the same B
+    "A": dict(B=32, C=256, N=2048, R=8, k=32, cab=8,
+              name="SoftPool fwd+bwd (B=32,N=2048,C=256,R=8,k=32,cab=8) + Chamfer fwd+bwd (B=32, 2048<->2048)"),
+    "A1": dict(B=32, C=256, N=2048, R=8, k=256, cab=8,
+               name="SoftPool fwd+bwd (B=32,N=2048,C=256,R=8,k=256,cab=8; reference operating point) + Chamfer (B=32, 2048<->2048)"),
+    "N8192": dict(B=32, C=256, N=8192, R=8, k=1024, cab=8,
+                  name="SoftPool fwd+bwd (B=32,N=8192,C=256,R=8,k=1024,cab=8) + Chamfer (B=32, 8192<->8192)"),
+}
+METRIC = "softpool_chamfer_fwd_bwd_throughput"
+UNIT = "Mpoints/s"
+K_PAD = 16     # MMA K of the tensor-core distance formulation
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def algorithmic_bytes(w):
+    """algorithmic bytes of SoftPool fwd / bwd (keys in, dense grad_x out)."""
+    B, C, N, R, k, cab = (w[x] for x in "B C N R k cab".split())
+    fwd = 4 * B * R * N + 4 * B * C * R * k * 2 + 4 * B * (R + 3) * R * k + 4 * B * C * R * cab + 8 * B * N
+    bwd = 4 * B * C * R * k + 4 * B * C * R * cab + 4 * B * R * k + 4 * B * C * N
+    return fwd, bwd
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks (pynvml poller; nvidia-smi is too coarse for a sub-second timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok = [], set(), False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_mhz = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=2)
+        return dict(sm_mhz=(statistics.median(self.samples) if self.samples else None), sm_max_mhz=self.max_mhz,
+                    reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident step through the C ABI (preallocated buffers, capturable in a CUDA graph)
+# ---------------------------------------------------------------------------------------------
+class BufferSet:
+    def __init__(self, w, dev, seed):
+        import torch
+        B, C, N, R, k, cab = (w[x] for x in "B C N R k cab".split())
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        r = lambda *s: torch.randn(*s, generator=g).to(dev)
+        u = lambda *s: (torch.rand(*s, generator=g) - 0.5).to(dev)
+        self.x, self.keys = r(B, C, N), r(B, R, N)
+        self.g_cube, self.g_cab = r(B, C, R, k), r(B, C, R, cab)
+        self.xyz1, self.xyz2 = u(B, N, 3), u(B, N, 3)
+        e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+        self.idx = e(B, R, k, dt=torch.int32); self.sp_idx = e(B, R + 3, R, k); self.id_activa = e(B, N, dt=torch.int64)
+        self.sp_cube = e(B, C, R, k); self.cabins = e(B, C, R, cab); self.cab_arg = e(B, C, R, cab, dt=torch.uint16)
+        self.grad_x = e(B, C, N)
+        self.d1, self.d2 = e(B, N), e(B, N)
+        self.i1, self.i2 = e(B, N, dt=torch.int32), e(B, N, dt=torch.int32)
+        self.loss = e(B)
+        self.gd1 = torch.full((B, N), 1.0 / (N * B), device=dev); self.gd2 = torch.full((B, N), 1.0 / (N * B), device=dev)
+        self.gx1, self.gx2 = e(B, N, 3), e(B, N, 3)
+
+    def footprint(self):
+        import torch
+        return sum(v.numel() * v.element_size() for v in vars(self).values() if isinstance(v, torch.Tensor))
+
+
+KERNELS = ["sp_topk_f32", "sp_gather_fwd_f32", "sp_gather_bwd_f32", "chamfer_fwd_f32", "chamfer_loss_f32", "chamfer_bwd_f32"]
+LAUNCHES_PER_STEP = 7     # chamfer_bwd_f32 is two kernels (direct + scatter)
+
+
+class Step:
+    def __init__(self, w, dev):
+        import torch
+        from softpool_b200 import _lib
+        self.w, self.dev, self.L, self.lib = w, dev, _lib.lib(), _lib
+        B, N = w["B"], w["N"]
+        self.ws_bytes = int(self.L.chamfer_fwd_workspace_bytes(B, N, N))
+        self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev)
+
+    def calls(self, s):
+        """[(name, thunk)] in launch order for buffer set s, on the current stream."""
+        import torch
+        L, p, chk, w = self.L, self.lib.ptr, self.lib.check, self.w
+        B, C, N, R, k, cab = (w[x] for x in "B C N R k cab".split())
+        st = lambda: ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        return [
+            ("sp_topk_f32", lambda: chk(L.sp_topk_f32(p(s.keys), B, R, N, k, p(s.idx), p(s.sp_idx), p(s.id_activa), st()), "sp_topk_f32")),
+            ("sp_gather_fwd_f32", lambda: chk(L.sp_gather_fwd_f32(p(s.x), p(s.idx), B, C, N, R, k, cab, p(s.sp_cube), p(s.cabins), p(s.cab_arg), st()), "sp_gather_fwd_f32")),
+            ("sp_gather_bwd_f32", lambda: chk(L.sp_gather_bwd_f32(p(s.g_cube), p(s.g_cab), p(s.idx), p(s.cab_arg), B, C, N, R, k, cab, p(s.grad_x), st()), "sp_gather_bwd_f32")),
+            ("chamfer_fwd_f32", lambda: chk(L.chamfer_fwd_f32(p(s.xyz1), p(s.xyz2), B, N, N, p(s.d1), p(s.d2), p(s.i1), p(s.i2), p(self.ws), self.ws_bytes, st()), "chamfer_fwd_f32")),
+            ("chamfer_loss_f32", lambda: chk(L.chamfer_loss_f32(p(s.d1), p(s.d2), B, N, N, p(s.loss), st()), "chamfer_loss_f32")),
+            ("chamfer_bwd_f32", lambda: chk(L.chamfer_bwd_f32(p(s.xyz1), p(s.xyz2), p(s.gd1), p(s.gd2), p(s.i1), p(s.i2), B, N, N, p(s.gx1), p(s.gx2), st()), "chamfer_bwd_f32")),
+        ]
+
+    def run(self, s):
+        for _, f in self.calls(s):
+            f()
+
+
+def run_b200(args, w, rank, local_rank, world):
+    import torch
+    from softpool_b200 import dist as spd
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+    step = Step(w, dev)
+    one = BufferSet(w, dev, 1234 + rank)
+    nsets = max(3, int(-(-400e6 // one.footprint())))             # rotating footprint >= 400 MB > 126 MB L2
+    sets = [one] + [BufferSet(w, dev, 1235 + rank + 97 * i) for i in range(1, nsets)]
+    B, N = w["B"], w["N"]
+
+    # ---- CUDA graphs: one per buffer set --------------------------------------------------------
+    stream = torch.cuda.Stream(device=dev)
+    graphs = []
+    with torch.cuda.stream(stream):
+        for s in sets:
+            step.run(s)                                            # warm (sets func attributes) before capture
+        stream.synchronize()
+        for s in sets:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                step.run(s)
+            graphs.append(g)
+    torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            graphs[i % nsets].replay()
+        stream.synchronize()
+        spd.barrier()
+        torch.cuda.synchronize(dev)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(args.steps):
+            graphs[i % nsets].replay()
+        e1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize(dev)
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        clocks = sampler.stop()
+        spd.barrier()
+    dev_ms = e0.elapsed_time(e1)
+    ms_per_step = spd.max_over_ranks(dev_ms, dev) / args.steps
+    points_per_step = spd.sum_over_ranks(B * N, dev)
+    value = points_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---- instrumented pass: per-kernel CUDA-event times, L2 flushed before every step --------------
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    n_inst = max(10, min(args.steps, 50))
+    per = {k: [] for k in KERNELS}
+    with torch.cuda.stream(stream):
+        evs = []
+        for i in range(n_inst):
+            s = sets[i % nsets]
+            flush.zero_(); flush.add_(1.0)                         # evict L2 and let the CPU run ahead
+            row = [torch.cuda.Event(enable_timing=True)]
+            row[0].record(stream)
+            for name, f in step.calls(s):
+                f()
+                ev = torch.cuda.Event(enable_timing=True); ev.record(stream); row.append(ev)
+            evs.append(row)
+        stream.synchronize()
+    for row in evs[2:]:
+        for j, name in enumerate(KERNELS):
+            per[name].append(row[j].elapsed_time(row[j + 1]) * 1e3)          # us
+    kern_us = {k: statistics.median(v) for k, v in per.items()}
+    fwd_b, bwd_b = algorithmic_bytes(w)
+    P = B * N * N
+    sp_us = kern_us["sp_topk_f32"] + kern_us["sp_gather_fwd_f32"] + kern_us["sp_gather_bwd_f32"]
+    ch_us = kern_us["chamfer_fwd_f32"] + kern_us["chamfer_loss_f32"] + kern_us["chamfer_bwd_f32"]
+    roof_sp = dict(bound="hbm", kernels="sp_topk_f32+sp_gather_fwd_f32+sp_gather_bwd_f32",
+                   achieved=(fwd_b + bwd_b) / (sp_us * 1e-6) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
+                   algorithmic_bytes=fwd_b + bwd_b, us=sp_us, traffic=None, peak_source=peaks["source"])
+    roof_sp["frac"] = roof_sp["achieved"] / roof_sp["peak"]
+    roof_ch = dict(bound="tensor", kernels="chamfer_fwd_f32",
+                   achieved=2.0 * P * K_PAD / (kern_us["chamfer_fwd_f32"] * 1e-6) / 1e12, peak=peaks["bf16_tflops"],
+                   unit="TFLOP/s", issued_flops=2.0 * P * K_PAD, algorithmic_flops=8.0 * P,
+                   direct_form_tflops=8.0 * P / (kern_us["chamfer_fwd_f32"] * 1e-6) / 1e12,
+                   us=kern_us["chamfer_fwd_f32"], traffic=None, peak_source=peaks["source"],
+                   note="exact fp32 FMA path (round 1); achieved counts the K=16 tensor formulation's flops")
+    roof_ch["frac"] = roof_ch["achieved"] / roof_ch["peak"]
+    dominant = roof_ch if kern_us["chamfer_fwd_f32"] >= max(kern_us["sp_gather_fwd_f32"], kern_us["sp_gather_bwd_f32"]) else roof_sp
+
+    # ---- e2e: public API, pinned host inputs, H2D + D2H inside the timed region -----------------------
+    e2e = run_e2e(args, w, dev, stream, spd)
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "per_gpu_batch": B, "points_per_step": int(points_per_step),
+                       "timing": "CUDA events around %d CUDA-graph replays, max over ranks" % args.steps,
+                       "l2": "inputs rotate over %d buffer sets (%.0f MB > 126 MB L2)" % (nsets, nsets * one.footprint() / 1e6),
+                       "wall_ms_per_step": wall_ms / args.steps, "parallelism": "batch-sharded, no data-path collective"},
+            "roofline": dominant, "roofline_softpool": roof_sp, "roofline_chamfer": roof_ch,
+            "kernel_us": kern_us, "softpool_fwd_bwd_us": sp_us, "chamfer_fwd_bwd_us": ch_us,
+            "kernel_timing": "median of %d instrumented steps, CUDA events between launches, 256 MB L2 flush before each step" % (n_inst - 2),
+            "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "clocks": clocks,
+        }
+    return out
+
+
+def run_e2e(args, w, dev, stream, spd):
+    import torch
+    import softpool_b200 as spb
+    from softpool_b200 import ops
+    B, C, N, R, k, cab = (w[x] for x in "B C N R k cab".split())
+    g = torch.Generator().manual_seed(7)
+    pin = lambda t: t.pin_memory()
+    hx, hk = pin(torch.randn(B, C, N, generator=g)), pin(torch.randn(B, R, N, generator=g))
+    hgc, hgb = pin(torch.randn(B, C, R, k, generator=g)), pin(torch.randn(B, C, R, cab, generator=g))
+    h1, h2 = pin(torch.rand(B, N, 3, generator=g) - 0.5), pin(torch.rand(B, N, 3, generator=g) - 0.5)
+    out_cab = pin(torch.empty(B, C, R, cab)); out_loss = pin(torch.empty(B)); out_g1 = pin(torch.empty(B, N, 3))
+    cd = spb.chamferDist()
+    h2d = sum(t.numel() * t.element_size() for t in (hx, hk, hgc, hgb, h1, h2))
+    d2h = sum(t.numel() * t.element_size() for t in (out_cab, out_loss, out_g1))
+
+    def one():
+        x = hx.to(dev, non_blocking=True).requires_grad_(True)
+        keys = hk.to(dev, non_blocking=True)
+        gc, gb = hgc.to(dev, non_blocking=True), hgb.to(dev, non_blocking=True)
+        a = h1.to(dev, non_blocking=True).requires_grad_(True)
+        b = h2.to(dev, non_blocking=True)
+        idx, sp_idx, id_activa = ops.softpool_topk(keys, k)
+        sp_cube, cabins = ops.softpool_gather(x, idx, cab)
+        torch.autograd.backward([sp_cube, cabins], [gc, gb])
+        d1, d2, _, _ = cd(a, b)
+        loss = d1.mean(1) + d2.mean(1)
+        loss.mean().backward()
+        out_cab.copy_(cabins.detach(), non_blocking=True)
+        out_loss.copy_(loss.detach(), non_blocking=True)
+        out_g1.copy_(a.grad, non_blocking=True)
+
+    steps = max(5, min(args.steps, 30))
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            one()
+        stream.synchronize()
+        spd.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            one()
+        e1.record(stream)
+        stream.synchronize()
+    ms = spd.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    pts = spd.sum_over_ranks(B * N, dev)
+    return {"value": pts / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "api": "ops.softpool_topk + ops.softpool_gather (autograd) + chamferDist (autograd), pinned host tensors"}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU port of the reference path (cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------------------------
+class CpuPort:
+    def __init__(self, w, Bs, seed=99):
+        import numpy as np
+        import torch
+        self.np, self.torch = np, torch
+        from oracle import chamfer_oracle as co
+        from oracle import softpool_torch_port as port
+        self.co, self.port = co, port
+        self.threads = co.default_threads()
+        torch.set_num_threads(self.threads)
+        C, N, R, k, cab = (w[x] for x in "C N R k cab".split())
+        g = torch.Generator().manual_seed(seed)
+        self.k, self.cab, self.Bs, self.N = k, cab, Bs, N
+        self.x, self.keys = torch.randn(Bs, C, N, generator=g), torch.randn(Bs, R, N, generator=g)
+        self.gc, self.gb = torch.randn(Bs, C, R, k, generator=g), torch.randn(Bs, C, R, cab, generator=g)
+        self.a = (torch.rand(Bs, N, 3, generator=g) - 0.5).numpy()
+        self.b = (torch.rand(Bs, N, 3, generator=g) - 0.5).numpy()
+        self.g1 = np.full((Bs, N), 1.0 / (N * Bs), np.float32)
+
+    def step(self):
+        self.port.forward_backward(self.x, self.keys, self.k, self.cab, self.gc, self.gb)
+        d1, d2, i1, i2 = self.co.forward(self.a, self.b, self.threads)
+        _ = d1.mean(1) + d2.mean(1)
+        self.co.backward(self.a, self.b, self.g1, self.g1, i1, i2, self.threads)
+
+
+def cpu_baseline(w, budget_s=20.0):
+    probe = CpuPort(w, 2)
+    probe.step()                                     # first call pays one-time init
+    t = time.perf_counter(); probe.step(); t1 = (time.perf_counter() - t) / 2
+    Bs = int(max(1, min(w["B"], budget_s / 4.0 / max(t1, 1e-4))))
+    port = CpuPort(w, Bs)
+    port.step()
+    ts = []
+    for _ in range(3):
+        t = time.perf_counter(); port.step(); ts.append(time.perf_counter() - t)
+    best = min(ts)
+    return {"value": Bs * w["N"] / best / 1e6, "unit": UNIT, "cores": port.threads, "kind": "port",
+            "sample": "%d of %d clouds of the same workload, best of 3 steps after 1 warm-up (%.3f s/step); torch CPU port of softpool.py:134-151 + C restatement of chamfer.cu, %d threads" % (Bs, w["B"], best, port.threads)}
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return None
+    probe = CpuPort(w, 2)
+    probe.step()                                     # first call pays one-time init
+    t = time.perf_counter(); probe.step(); t1 = (time.perf_counter() - t) / 2
+    budget = 150.0
+    Bs = int(max(1, min(w["B"], budget / max(1, args.steps + args.warmup) / max(t1, 1e-4))))
+    port = CpuPort(w, Bs)
+    for _ in range(args.warmup):
+        port.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        port.step()
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    v = Bs * w["N"] / (ms * 1e-3) / 1e6
+    sample = "%d of %d clouds per step (bounded sample), torch CPU port of the reference SoftPool loop + C restatement of the reference Chamfer kernels" % (Bs, w["B"])
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": w["name"], "per_step_clouds": Bs},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": port.threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    w = WORKLOADS[args.workload]
+
+    from softpool_b200 import dist as spd
+    rank, local_rank, world = spd.env_world()
+    if args.impl == "reference":
+        out = run_reference(args, w, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return 0
+    rank, local_rank, world = spd.init()
+    out = run_b200(args, w, rank, local_rank, world)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(w)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

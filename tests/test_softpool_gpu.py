@@ -1,0 +1,250 @@
+"""GPU parity: the sm_100a SoftPool path (through the C ABI) against the golden outputs of the
+reference softpool.py and against the numpy oracle on seeded inputs; size-independent properties
+at BASELINE.json's full size."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_cases
+from oracle import softpool_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+RTOL_GRAD = 1e-4      # north_star: "within 1e-4 rel for the pooled features"; indices are bit-exact
+ATOL_GRAD = 1e-6
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def run_cuda(x, keys, k, cab, g_cube=None, g_cabins=None):
+    from softpool_b200 import ops
+    xt = torch.from_numpy(np.ascontiguousarray(x)).to(dev()).requires_grad_(True)
+    kt = torch.from_numpy(np.ascontiguousarray(keys)).to(dev())
+    idx, sp_idx, id_activa = ops.softpool_topk(kt, k)
+    sp_cube, cabins = ops.softpool_gather(xt, idx, cab)
+    out = dict(idx=idx.cpu().numpy(), sp_idx=sp_idx.cpu().numpy(), id_activa=id_activa.cpu().numpy(),
+               sp_cube=sp_cube.detach().cpu().numpy(), cabins=cabins.detach().cpu().numpy())
+    if g_cube is not None:
+        gc = torch.from_numpy(g_cube).to(dev())
+        gb = torch.from_numpy(g_cabins).to(dev())
+        torch.autograd.backward([sp_cube, cabins], [gc, gb])
+        out["grad_x"] = xt.grad.cpu().numpy()
+    return out
+
+
+@pytest.mark.parametrize("case", golden_cases("softpool"))
+def test_golden_reference_outputs(case):
+    g = np.load(os.path.join(GOLDEN, "softpool_%s.npz" % case))
+    B, C, N, R, sp_ratio, cab, k, tie_free = [int(v) for v in g["meta"]]
+    out = run_cuda(g["x"], g["keys"], k, cab, g["g_cube"], g["g_cabins"])
+    pre = "" if tie_free else "st_"      # tie fixtures: reference run with torch.sort(stable=True)
+    assert out["sp_idx"].dtype == np.float32 and out["id_activa"].dtype == np.int64
+    assert np.array_equal(out["sp_idx"], g[pre + "sp_idx"])                       # bit-exact indices
+    assert np.array_equal(out["id_activa"], g["id_activa"])
+    assert np.array_equal(bits(out["sp_cube"]), bits(g[pre + "sp_cube"]))         # bit-exact copies
+    assert np.array_equal(bits(out["cabins"]), bits(g[pre + "cabins"]))
+    np.testing.assert_allclose(out["grad_x"], g[pre + "grad_x"], rtol=RTOL_GRAD, atol=ATOL_GRAD)
+    if not tie_free:
+        # the unmodified reference picked the same key values slot by slot
+        ref_idx = g["sp_idx"][:, 0].astype(np.int64)
+        ku = so.order_key(g["keys"])
+        assert np.array_equal(np.take_along_axis(ku, out["idx"].astype(np.int64), -1),
+                              np.take_along_axis(ku, ref_idx, -1))
+
+
+SEEDED = [
+    # B, C, N, R, k, cab
+    (4, 32, 512, 8, 64, 8),          # BASELINE config 1
+    (2, 64, 2048, 8, 256, 8),        # reference operating point R*k == N
+    (2, 64, 2048, 8, 32, 8),         # BASELINE config 2 shape (k=32), reduced B, C
+    (2, 16, 2048, 16, 128, 8),       # class default R=16
+    (1, 8, 8192, 8, 1024, 8),
+    (1, 4, 16384, 8, 2048, 8),       # largest supported row
+    (1, 4, 16384, 2, 16384, 8),      # full sort of the largest row
+    (2, 3, 1000, 3, 100, 7),         # nothing a power of two; cab 7 -> window 14, 2 trailing slots
+    (2, 5, 301, 3, 60, 8),
+    (3, 2, 9, 2, 9, 9),              # tiny, k == N == cab
+    (2, 4, 5, 1, 1, 1),              # k = 1
+    (1, 1, 1, 1, 1, 1),              # the smallest problem
+    (2, 8, 4096, 4, 5, 5),           # k << N, k not a power of two
+    (2, 8, 3000, 4, 750, 10),
+    (1, 256, 2048, 8, 32, 8),        # full C of config 2
+    (1, 512, 2048, 8, 256, 8),       # C sweep top end
+]
+
+
+@pytest.mark.parametrize("B,C,N,R,k,cab", SEEDED)
+@pytest.mark.parametrize("quant", [0, 8])
+def test_seeded_vs_oracle(B, C, N, R, k, cab, quant):
+    rng = np.random.default_rng(1000 * N + 10 * C + R + quant)
+    x = rng.standard_normal((B, C, N), dtype=np.float32)
+    keys = rng.standard_normal((B, R, N), dtype=np.float32)
+    if quant:                                   # tie stress: keys and features on a coarse grid
+        keys = np.round(keys * quant) / quant
+        x = np.round(x * quant) / quant
+    g_cube = rng.standard_normal((B, C, R, k), dtype=np.float32)
+    g_cabins = rng.standard_normal((B, C, R, cab), dtype=np.float32)
+    ref = so.softpool_forward(x, keys, k, cab)
+    ref_grad = so.softpool_backward(g_cube, g_cabins, ref["idx"], ref["cab_arg"], N)
+    out = run_cuda(x, keys, k, cab, g_cube, g_cabins)
+    assert np.array_equal(out["idx"], ref["idx"])
+    assert np.array_equal(out["sp_idx"], ref["sp_idx"])
+    assert np.array_equal(out["id_activa"], ref["id_activa"])
+    assert np.array_equal(bits(out["sp_cube"]), bits(ref["sp_cube"]))
+    assert np.array_equal(bits(out["cabins"]), bits(ref["cabins"]))
+    # same summation order as the oracle (ascending region) -> bit-exact, not just 1e-4
+    assert np.array_equal(bits(out["grad_x"]), bits(ref_grad))
+
+
+def test_special_values():
+    rng = np.random.default_rng(7)
+    B, C, N, R, k, cab = 2, 4, 512, 4, 128, 8
+    keys = rng.standard_normal((B, R, N), dtype=np.float32)
+    keys[0, 0, :] = 3.0
+    keys[0, 1, [5, 77, 300]] = np.nan
+    keys[0, 1, [9, 11]] = np.inf
+    keys[0, 1, 10] = -np.inf
+    keys[0, 2, ::2] = 0.0
+    keys[0, 2, 1::2] = -0.0
+    keys[1, 0, 3] = np.nan
+    keys[1, 3, 3] = np.nan
+    x = rng.standard_normal((B, C, N), dtype=np.float32)
+    x[0, 0, :40] = np.nan
+    x[0, 1, ::3] = -0.0
+    x[1, 2, :] = np.inf
+    ref = so.softpool_forward(x, keys, k, cab)
+    out = run_cuda(x, keys, k, cab)
+    assert np.array_equal(out["idx"], ref["idx"])
+    assert np.array_equal(out["id_activa"], ref["id_activa"])
+    assert np.array_equal(bits(out["sp_cube"]), bits(ref["sp_cube"]))
+    assert np.array_equal(bits(out["cabins"]), bits(ref["cabins"]))
+
+
+def test_module_matches_oracle_and_reference_surface():
+    """SoftPool nn.Module: same outputs as the oracle given the keys its own Sorter conv produced;
+    shapes / dtypes / parameter names of reference softpool.py:99-171."""
+    import softpool_b200 as spb
+    torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, C, N, R, ratio, cab = 4, 32, 512, 8, 8, 8
+    m = spb.SoftPool(regions=R, cabins=cab, sp_ratio=ratio, size_feat=C).to(dev())
+    x = torch.randn(B, C, N).to(dev()).requires_grad_(True)
+    sp_cube, sp_idx, cabins, id_activa = m(x)
+    k = N // ratio
+    assert sp_cube.shape == (B, C, R, k) and sp_idx.shape == (B, R + 3, R, k)
+    assert cabins.shape == (B, C, R, cab) and id_activa.shape == (B, N)
+    assert sp_idx.dtype == torch.float32 and id_activa.dtype == torch.int64
+    with torch.no_grad():
+        keys = m.sorter.conv1d(x).cpu().numpy()
+    ref = so.softpool_forward(x.detach().cpu().numpy(), keys, k, cab)
+    assert np.array_equal(sp_idx.cpu().numpy(), ref["sp_idx"])
+    assert np.array_equal(id_activa.cpu().numpy(), ref["id_activa"])
+    assert np.array_equal(bits(sp_cube.detach().cpu().numpy()), bits(ref["sp_cube"]))
+    assert np.array_equal(bits(cabins.detach().cpu().numpy()), bits(ref["cabins"]))
+    (sp_cube.sum() + 2 * cabins.sum()).backward()
+    # no gradient reaches the sorter / dead convs
+    assert all(p.grad is None for p in m.parameters())
+    ref_grad = so.softpool_backward(np.ones_like(ref["sp_cube"]), 2 * np.ones_like(ref["cabins"]),
+                                    ref["idx"], ref["cab_arg"], N)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), ref_grad, rtol=RTOL_GRAD, atol=ATOL_GRAD)
+    names = {n: tuple(p.shape) for n, p in m.state_dict().items()}
+    assert names == {
+        "conv2d_1.weight": (C, C, 1, 3), "conv2d_1.bias": (C,),
+        "conv2d_2.weight": (C, C, 1, 3), "conv2d_2.bias": (C,),
+        "conv2d_3.weight": (C, C, 1, cab - 4), "conv2d_3.bias": (C,),
+        "conv2d_5.weight": (C, C, R, 1), "conv2d_5.bias": (C,),
+        "sorter.conv1d.weight": (R, C, 1), "sorter.conv1d.bias": (R,),
+    }
+
+
+def test_softpoolfeat_surface():
+    import softpool_b200 as spb
+    torch.manual_seed(1)
+    R, ratio = 8, 8
+    m = spb.SoftPoolFeat(num_points=2048, regions=R, sp_points=2048, sp_ratio=ratio).to(dev())
+    x = (torch.rand(2, 3, 2048) - 0.5).to(dev())
+    sp_cube, cabins, sp_idx = m(x)
+    assert sp_cube.shape == (2, 256, 1, R * (2048 // ratio))
+    assert cabins.shape == (2, 256, R, 8)
+    assert sp_idx.shape == (2, R + 3, 1, R * (2048 // ratio))
+    # the call site model.py:283-285 gathers the input points with sp_idx[:, :3]
+    chosen = torch.gather(x, dim=2, index=sp_idx[:, :3, 0, :].long())
+    assert chosen.shape == (2, 3, 2048)
+
+
+def test_train2cabins_standalone():
+    import softpool_b200 as spb
+    rng = np.random.default_rng(3)
+    w = np.round(rng.standard_normal((2, 3, 4, 50), dtype=np.float32) * 4) / 4
+    wt = torch.from_numpy(w).to(dev()).requires_grad_(True)
+    cab = spb.train2cabins(wt, 8)
+    ref, ref_arg = so.window_argmax(w, 8)
+    assert np.array_equal(bits(cab.detach().cpu().numpy()), bits(ref))
+    g = rng.standard_normal(ref.shape, dtype=np.float32)
+    cab.backward(torch.from_numpy(g).to(dev()))
+    expect = np.zeros_like(w)
+    wl = 50 // 8
+    np.put_along_axis(expect, ref_arg.astype(np.int64) + 0, g, axis=-1)
+    assert ref_arg.max() < 8 * wl
+    assert np.array_equal(wt.grad.cpu().numpy(), expect)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 (B=32, N=2048, C=256, R=8, k=32) and the operating point k=256: properties
+    that do not need the (slow) oracle."""
+    from softpool_b200 import ops
+    torch.manual_seed(0)
+    B, C, N, R, cab = 32, 256, 2048, 8, 8
+    x = torch.randn(B, C, N, device=dev(), requires_grad=True)
+    keys = torch.randn(B, R, N, device=dev())
+    for k in (32, 256):
+        idx, sp_idx, id_activa = ops.softpool_topk(keys, k)
+        li = idx.long()
+        sel = torch.gather(keys, 2, li)
+        # sortedness (descending, ties by ascending index)
+        d = sel[..., 1:] - sel[..., :-1]
+        assert (d <= 0).all()
+        assert ((d < 0) | (li[..., 1:] > li[..., :-1])).all()
+        # it is THE top-k: exactly k keys are >= the k-th (random floats: no ties at the boundary)
+        kth = sel[..., -1:]
+        assert ((keys >= kth).sum(-1) == k).all()
+        assert torch.equal(id_activa, keys.argmax(1))
+        assert torch.equal(sp_idx, li[:, None].float().expand(B, R + 3, R, k))
+        sp_cube, cabins = ops.softpool_gather(x, idx, cab)
+        ref_cube = torch.gather(x.detach()[:, :, None, :].expand(B, C, R, N), 3, li[:, None].expand(B, C, R, k))
+        assert torch.equal(sp_cube, ref_cube)
+        wl = k // cab
+        assert torch.equal(cabins, ref_cube[..., :wl * cab].reshape(B, C, R, cab, wl).max(-1)[0])
+        # backward: linear in the upstream gradient and mass-preserving
+        g1, g2 = torch.randn_like(sp_cube), torch.randn_like(cabins)
+        (gx,) = torch.autograd.grad([sp_cube, cabins], x, [g1, g2], retain_graph=True)
+        (gx2,) = torch.autograd.grad([sp_cube, cabins], x, [2 * g1, 2 * g2], retain_graph=True)
+        assert torch.equal(gx2, 2 * gx)
+        torch.testing.assert_close(gx.sum(-1), g1.sum((-1, -2)) + g2.sum((-1, -2)), rtol=1e-4, atol=1e-3)
+        # against autograd of the reference composition (torch ops on the same GPU)
+        xr = x.detach().clone().requires_grad_(True)
+        cube_r = torch.gather(xr[:, :, None, :].expand(B, C, R, N), 3, li[:, None].expand(B, C, R, k))
+        cab_r = cube_r[..., :wl * cab].reshape(B, C, R, cab, wl).max(-1)[0]
+        torch.autograd.backward([cube_r, cab_r], [g1, g2])
+        torch.testing.assert_close(gx, xr.grad, rtol=RTOL_GRAD, atol=1e-5)
+
+
+def test_errors_are_loud():
+    from softpool_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.softpool_topk(torch.randn(1, 2, 8), 4)                       # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        ops.softpool_topk(torch.randn(1, 2, 8, device=dev()), 9)         # k > N
+    with pytest.raises(RuntimeError):
+        ops.softpool_topk(torch.randn(1, 1, 20000, device=dev()), 4)     # N > 16384 unsupported
+    with pytest.raises(RuntimeError):
+        ops.softpool_gather(torch.randn(1, 2, 8, device=dev()), torch.zeros(1, 1, 4, dtype=torch.int32, device=dev()), 5)
