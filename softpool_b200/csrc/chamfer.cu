@@ -6,6 +6,7 @@
 //     d = fma(dz, dz, fma(dx, dx, dy * dy)),  dx = x2 - x1 ...
 // and the first minimum wins, so dist/idx are bit-identical to the reference for finite inputs.
 #include "spk_common.cuh"
+#include <stdlib.h>
 
 namespace spk {
 
@@ -140,19 +141,26 @@ chamfer_loss_kernel(const float* __restrict__ dist1, const float* __restrict__ d
 
 }  // namespace spk
 
+// Pair blocks below this size are not worth the prep pass + tensor pipeline set-up.
+static bool use_tensor_path(int n, int m) {
+    if (n < 1 || m < 1) return false;
+    const char* e = getenv("SPK_CHAMFER_EXACT");           // debugging / A-B switch: force the FMA path
+    if (e && e[0] == '1') return false;
+    return (long long)n * m >= 256LL * 256LL;
+}
+
 extern "C" size_t chamfer_fwd_workspace_bytes(int B, int n, int m) {
-    (void)B; (void)n; (void)m;
-    return 0;
+    if (B < 1 || n < 1 || m < 1) return 0;
+    return spk::chamfer_tc_workspace_bytes(B, n, m);
 }
 
 extern "C" int chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int n, int m,
                                float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* ws,
                                size_t ws_bytes, void* stream) {
     using namespace spk;
-    (void)ws; (void)ws_bytes;
     if (B < 0 || n < 0 || m < 0) return fail(SPK_E_BADARG, "chamfer_fwd_f32: negative size");
     if (B == 0 || (n == 0 && m == 0)) return SPK_OK;
-    if (!dist1 || !dist2 || !idx1 || !idx2) return fail(SPK_E_BADARG, "chamfer_fwd_f32: null output");
+    if ((n && (!dist1 || !idx1)) || (m && (!dist2 || !idx2))) return fail(SPK_E_BADARG, "chamfer_fwd_f32: null output");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0 || m == 0) {   // reference leaves its zero-initialised outputs untouched
         if (n) { SPK_CUDA(cudaMemsetAsync(dist1, 0, (size_t)B * n * 4, st)); SPK_CUDA(cudaMemsetAsync(idx1, 0, (size_t)B * n * 4, st)); }
@@ -161,6 +169,7 @@ extern "C" int chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int 
     }
     if (!xyz1 || !xyz2) return fail(SPK_E_BADARG, "chamfer_fwd_f32: null input");
     if (B > 65535) return fail(SPK_E_UNSUPPORTED, "chamfer_fwd_f32: B=%d > 65535", B);
+    if (use_tensor_path(n, m)) return chamfer_tc_forward(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, ws, ws_bytes, st);
     const int per = CH_THREADS * CH_QPT;
     dim3 grid((max(n, m) + per - 1) / per, B, 2);
     chamfer_nn_exact_kernel<<<grid, CH_THREADS, 0, st>>>(xyz1, xyz2, n, m, dist1, dist2, idx1, idx2);

@@ -1,0 +1,441 @@
+// chamfer_tc.cu -- Chamfer forward on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces NmDistanceKernel x2 (reference distance/chamfer/chamfer.cu:12-143) and returns
+// bit-identical dist/idx for finite inputs, yet evaluates the n x m pair block on the tensor pipe.
+//
+// Idea.  The pairwise block IS a dense contraction:  d(p,q) = |p|^2 + |q|^2 - 2 p.q.  With fp16
+// hi/lo splits of the (centred, power-of-two scaled) coordinates and 3-way fp16 splits of the
+// norms, ONE K=16 MMA row pair produces the squared distance in fp32 with absolute error
+// e <= ~2^-17 (scaled units):
+//     A'(p) = [-2xh,-2xh,-2xl, -2yh,-2yh,-2yl, -2zh,-2zh,-2zl,  nh,nm,nl,  1,1,1,  0]
+//     B'(q) = [  xh,  xl,  xh,   yh,  yl,  yh,   zh,  zl,  zh,   1, 1, 1,  mh,mm,ml, 0]
+// The approximate block only FILTERS: per query row the epilogue keeps the minimum of every
+// 32-target chunk (one 3-input FMNMX3 per two elements -- the whole per-element cost), then only
+// chunks whose minimum is within tau = 2e of the row minimum are re-evaluated with the reference's
+// exact float32 expression  d = fma(dz,dz, fma(dx,dx, dy*dy))  and first-minimum tie rule.  A chunk
+// that holds the true nearest neighbour always passes the filter (its approximate distance is
+// <= d_true + e <= d_any + e <= approx_any + 2e), so the result equals the brute-force one.
+//
+// Kernel structure (one CTA = 128 queries of one sample and direction, 2 CTAs per SM):
+//   warp 0   TMA producer: A tile (128 x 32 B) once, B tiles (128 targets x 32 B) through a ring
+//   warp 1   TMEM alloc (256 columns = 2 accumulator buffers of 128) + single-thread tcgen05.mma
+//            issue (M=128, N=128, K=16, kind::f16, fp32 accumulate) + tcgen05.commit -> mbarriers
+//   warps 2-9  epilogue: tcgen05.ld 32x32b.x32 -> chunk minima in registers; every 2048 targets
+//            the filter + exact re-evaluation; final (dist, idx) store
+// Operands are pre-formatted by chamfer_prep_kernel in the canonical no-swizzle K-major layout
+// (8-row x 16-byte core matrices, LBO = 128 B, SBO = 256 B), so tiles move with 1-D bulk copies.
+#include "spk_common.cuh"
+#include <cuda_fp16.h>
+
+namespace spk {
+
+constexpr int TC_TILE = 128;            // queries per CTA = targets per MMA tile
+constexpr int TC_STAGES = 4;            // B-tile ring depth
+constexpr int TC_THREADS = 320;         // 10 warps
+constexpr int TC_SB_TILES = 16;         // tiles per super-block (2048 targets)
+constexpr int TC_TILE_BYTES = TC_TILE * 32;
+constexpr float TC_PAD_NORM = 30000.f;  // norm of padding targets: never the minimum
+
+struct ChamferMeta {                    // per sample, written by the prep kernel
+    float cx, cy, cz;                   // centre (bounding-box midpoint of both clouds)
+    float scale;                        // power of two: |(x - c) * scale| <= 1
+    float tau;                          // filter slack in scaled squared units
+    float scale2;                       // scale * scale
+    float pad0, pad1;
+};
+
+// ---------------------------------------------------------------------------------------------
+// prep: centre/scale per sample, fp16 split operands in UMMA canonical layout
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split2(float v, __half& h, __half& l) {
+    h = __float2half_rn(v);
+    l = __float2half_rn(v - __half2float(h));
+}
+__device__ __forceinline__ void split3(float v, __half& h, __half& m, __half& l) {
+    h = __float2half_rn(v);
+    const float r1 = v - __half2float(h);
+    m = __float2half_rn(r1);
+    l = __float2half_rn(r1 - __half2float(m));
+}
+
+// byte offset of row r's first 16-byte K-chunk inside an operand array
+__device__ __forceinline__ size_t op_row_offset(int r) { return (size_t)(r >> 3) * 256 + (size_t)(r & 7) * 16; }
+
+__device__ __forceinline__ void write_rows(unsigned char* opA, unsigned char* opB, int r, bool real,
+                                           float ux, float uy, float uz) {
+    __align__(16) __half a[16];
+    __align__(16) __half b[16];
+    if (real) {
+        __half xh, xl, yh, yl, zh, zl, nh, nm, nl;
+        split2(ux, xh, xl); split2(uy, yh, yl); split2(uz, zh, zl);
+        const float nrm = fmaf(uz, uz, fmaf(uy, uy, ux * ux));
+        split3(nrm, nh, nm, nl);
+        const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f), m2 = __float2half_rn(-2.f);
+        a[0] = __hmul(m2, xh); a[1] = a[0]; a[2] = __hmul(m2, xl);
+        a[3] = __hmul(m2, yh); a[4] = a[3]; a[5] = __hmul(m2, yl);
+        a[6] = __hmul(m2, zh); a[7] = a[6]; a[8] = __hmul(m2, zl);
+        a[9] = nh; a[10] = nm; a[11] = nl; a[12] = one; a[13] = one; a[14] = one; a[15] = zero;
+        b[0] = xh; b[1] = xl; b[2] = xh; b[3] = yh; b[4] = yl; b[5] = yh; b[6] = zh; b[7] = zl; b[8] = zh;
+        b[9] = one; b[10] = one; b[11] = one; b[12] = nh; b[13] = nm; b[14] = nl; b[15] = zero;
+    } else {
+        const __half zero = __float2half_rn(0.f), one = __float2half_rn(1.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { a[i] = zero; b[i] = zero; }
+        b[9] = one; b[12] = __float2half_rn(TC_PAD_NORM);     // a padding target is "infinitely" far
+    }
+    const size_t o = op_row_offset(r);
+    *reinterpret_cast<uint4*>(opA + o) = *reinterpret_cast<const uint4*>(&a[0]);
+    *reinterpret_cast<uint4*>(opA + o + 128) = *reinterpret_cast<const uint4*>(&a[8]);
+    *reinterpret_cast<uint4*>(opB + o) = *reinterpret_cast<const uint4*>(&b[0]);
+    *reinterpret_cast<uint4*>(opB + o + 128) = *reinterpret_cast<const uint4*>(&b[8]);
+}
+
+struct PrepParams {
+    const float* xyz1; const float* xyz2;
+    int n, m, n_pad, m_pad;
+    unsigned char* A1; unsigned char* B1; unsigned char* A2; unsigned char* B2;   // per sample n_pad*32 / m_pad*32 bytes
+    ChamferMeta* meta;
+};
+
+__global__ void __launch_bounds__(256)
+chamfer_prep_kernel(const PrepParams p) {
+    __shared__ float red[6][8];
+    __shared__ float s_meta[8];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const float* P = p.xyz1 + (size_t)b * p.n * 3;
+    const float* Q = p.xyz2 + (size_t)b * p.m * 3;
+    // bounding box over both clouds (every CTA of the sample recomputes it: 12*(n+m) bytes from L2)
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < p.n; i += 256)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = __ldg(P + 3 * i + a); lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    for (int i = tid; i < p.m; i += 256)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = __ldg(Q + 3 * i + a); lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        for (int d = 16; d > 0; d >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], d));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], d));
+        }
+    if ((tid & 31) == 0)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { red[a][tid >> 5] = lo[a]; red[3 + a][tid >> 5] = hi[a]; }
+    __syncthreads();
+    if (tid == 0) {
+        float L[3], H[3];
+        for (int a = 0; a < 3; ++a) {
+            L[a] = red[a][0]; H[a] = red[3 + a][0];
+            for (int w = 1; w < 8; ++w) { L[a] = fminf(L[a], red[a][w]); H[a] = fmaxf(H[a], red[3 + a][w]); }
+        }
+        float c[3], ext = 0.f, amax = 0.f;
+        for (int a = 0; a < 3; ++a) {
+            c[a] = 0.5f * L[a] + 0.5f * H[a];
+            ext = fmaxf(ext, fmaxf(H[a] - c[a], c[a] - L[a]));
+            amax = fmaxf(amax, fmaxf(fabsf(L[a]), fabsf(H[a])));
+        }
+        // scale = 2^-ceil(log2(ext)) so that |x - c| * scale <= 1; degenerate / non-finite boxes -> 1
+        float scale = 1.f;
+        if (ext > 0.f && ext < INFINITY) {
+            int e; (void)frexpf(ext, &e);                 // ext = f * 2^e, f in [0.5, 1)
+            e = max(-100, min(100, e));
+            scale = ldexpf(1.f, -e);
+        }
+        // error budget of the approximate block, scaled units: fp16 hi/lo products + fp32 accumulate
+        // (2^-17) plus the rounding of the centred coordinates themselves (|x| * 2^-23 * scale each)
+        const float delta = amax * scale * 1.1920929e-7f;
+        const float e_tot = 7.62939453125e-6f + 16.f * delta;
+        s_meta[0] = c[0]; s_meta[1] = c[1]; s_meta[2] = c[2]; s_meta[3] = scale;
+        s_meta[4] = 2.f * e_tot; s_meta[5] = scale * scale;
+        if (blockIdx.x == 0) {
+            ChamferMeta mm; mm.cx = c[0]; mm.cy = c[1]; mm.cz = c[2]; mm.scale = scale; mm.tau = 2.f * e_tot;
+            mm.scale2 = scale * scale; mm.pad0 = 0.f; mm.pad1 = 0.f;
+            p.meta[b] = mm;
+        }
+    }
+    __syncthreads();
+    const float cx = s_meta[0], cy = s_meta[1], cz = s_meta[2], sc = s_meta[3];
+    unsigned char* A1 = p.A1 + (size_t)b * p.n_pad * 32; unsigned char* B1 = p.B1 + (size_t)b * p.n_pad * 32;
+    unsigned char* A2 = p.A2 + (size_t)b * p.m_pad * 32; unsigned char* B2 = p.B2 + (size_t)b * p.m_pad * 32;
+    const int total = p.n_pad + p.m_pad;
+    for (int i = blockIdx.x * 256 + tid; i < total; i += gridDim.x * 256) {
+        const bool first = i < p.n_pad;
+        const int r = first ? i : i - p.n_pad;
+        const bool real = r < (first ? p.n : p.m);
+        float ux = 0.f, uy = 0.f, uz = 0.f;
+        if (real) {
+            const float* s = (first ? P : Q) + 3 * (size_t)r;
+            ux = (__ldg(s) - cx) * sc; uy = (__ldg(s + 1) - cy) * sc; uz = (__ldg(s + 2) - cz) * sc;
+        }
+        write_rows(first ? A1 : A2, first ? B1 : B2, r, real, ux, uy, uz);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t umma_smem_desc(const void* smem_ptr) {
+    // K-major, SWIZZLE_NONE (interleaved 8x16B core matrices): LBO = 128 B between the two K chunks,
+    // SBO = 256 B between 8-row groups, descriptor version 1 (sm_100)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem_ptr) >> 4) & 0x3FFF);
+    d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((256u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// kind::f16: A, B = F16 (0), D = F32 (1), both K-major, M = 128, N = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float min32(const float* v) {
+    float m0 = min3(v[0], v[1], v[2]), m1 = min3(v[3], v[4], v[5]), m2 = min3(v[6], v[7], v[8]), m3 = min3(v[9], v[10], v[11]);
+    m0 = min3(m0, v[12], v[13]); m1 = min3(m1, v[14], v[15]); m2 = min3(m2, v[16], v[17]); m3 = min3(m3, v[18], v[19]);
+    m0 = min3(m0, v[20], v[21]); m1 = min3(m1, v[22], v[23]); m2 = min3(m2, v[24], v[25]); m3 = min3(m3, v[26], v[27]);
+    m0 = min3(m0, v[28], v[29]); m1 = min3(m1, v[30], v[31]);
+    return fminf(min3(m0, m1, m2), m3);
+}
+__device__ __forceinline__ float ref_sqdist_tc(float x1, float y1, float z1, float x2, float y2, float z2) {
+    const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+struct TcParams {
+    const float* xyz1; const float* xyz2;
+    const unsigned char* A1; const unsigned char* B1; const unsigned char* A2; const unsigned char* B2;
+    const ChamferMeta* meta;
+    float* dist1; float* dist2; int32_t* idx1; int32_t* idx2;
+    int n, m, n_pad, m_pad;
+    int tiles1, tiles2;      // query tiles per sample in direction 0 / 1
+};
+
+struct __align__(128) TcSmem {
+    unsigned char a_tile[TC_TILE_BYTES];
+    unsigned char b_tile[TC_STAGES][TC_TILE_BYTES];
+    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full, tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+    float rowmin[2][2][TC_TILE];          // [super-block parity][column half][row]
+    float best_d[TC_TILE]; int best_i[TC_TILE];
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+chamfer_tc_kernel(const TcParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // which (direction, sample, query tile)
+    int job = blockIdx.x;
+    const int b = blockIdx.y;
+    const int dir = job < p.tiles1 ? 0 : 1;
+    if (dir) job -= p.tiles1;
+    const int nq = dir ? p.m : p.n, nt = dir ? p.n : p.m;
+    const int nq_pad = dir ? p.m_pad : p.n_pad, nt_pad = dir ? p.n_pad : p.m_pad;
+    const float* Qx = (dir ? p.xyz2 : p.xyz1) + (size_t)b * nq * 3;
+    const float* Tx = (dir ? p.xyz1 : p.xyz2) + (size_t)b * nt * 3;
+    const unsigned char* Aop = (dir ? p.A2 : p.A1) + ((size_t)b * nq_pad + (size_t)job * TC_TILE) * 32;
+    const unsigned char* Bop = (dir ? p.B1 : p.B2) + (size_t)b * nt_pad * 32;
+    float* dist = (dir ? p.dist2 : p.dist1) + (size_t)b * nq;
+    int32_t* idx = (dir ? p.idx2 : p.idx1) + (size_t)b * nq;
+    const int T = nt_pad / TC_TILE;                        // target tiles
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+        mbar_init(&S.a_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], 8); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {   // TMEM: 256 columns (2 x 128-column fp32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(&S.a_full, TC_TILE_BYTES);
+            bulk_g2s(S.a_tile, Aop, TC_TILE_BYTES, &S.a_full);
+            for (int t = 0; t < T; ++t) {
+                const int s = t % TC_STAGES;
+                mbar_wait(&S.empty[s], (uint32_t)(((t / TC_STAGES) & 1) ^ 1));
+                mbar_expect_tx(&S.full[s], TC_TILE_BYTES);
+                bulk_g2s(S.b_tile[s], Bop + (size_t)t * TC_TILE_BYTES, TC_TILE_BYTES, &S.full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            mbar_wait(&S.a_full, 0);
+            const uint64_t a_desc = umma_smem_desc(S.a_tile);
+            for (int t = 0; t < T; ++t) {
+                const int s = t % TC_STAGES, buf = t & 1;
+                mbar_wait(&S.tmem_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1));
+                mbar_wait(&S.full[s], (uint32_t)((t / TC_STAGES) & 1));
+                tc_fence_after();
+                umma_f16(tmem_base + (uint32_t)buf * TC_TILE, a_desc, umma_smem_desc(S.b_tile[s]), TC_IDESC);
+                umma_commit(&S.empty[s]);            // smem slot free once the MMA has read it
+                umma_commit(&S.tmem_full[buf]);      // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: 8 warps; warp%4 picks the TMEM lane quarter, (warp-2)/4 the column half =====
+        const int q = warp & 3, h = (warp - 2) >> 2;
+        const int row = q * 32 + lane;                         // query row inside the tile
+        const int gq = job * TC_TILE + row;                    // query index inside the cloud
+        const bool live = gq < nq;
+        const ChamferMeta mt = p.meta[b];
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        if (live) { qx = __ldg(Qx + 3 * (size_t)gq); qy = __ldg(Qx + 3 * (size_t)gq + 1); qz = __ldg(Qx + 3 * (size_t)gq + 2); }
+        // reference: the first target initialises the running best (`k==0 || d<best`, chamfer.cu:36)
+        float best_d = ref_sqdist_tc(qx, qy, qz, __ldg(Tx), __ldg(Tx + 1), __ldg(Tx + 2));
+        int best_i = 0;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 64;
+
+        const int n_sb = (T + TC_SB_TILES - 1) / TC_SB_TILES;
+        for (int sb = 0; sb < n_sb; ++sb) {
+            float cm[2 * TC_SB_TILES];
+#pragma unroll
+            for (int tt = 0; tt < TC_SB_TILES; ++tt) {
+                const int t = sb * TC_SB_TILES + tt;
+                cm[2 * tt] = INFINITY; cm[2 * tt + 1] = INFINITY;
+                if (t < T) {
+                    const int buf = t & 1;
+                    mbar_wait(&S.tmem_full[buf], (uint32_t)((t >> 1) & 1));
+                    tc_fence_after();
+                    float v0[32], v1[32];
+                    tmem_ld32(lane_addr + (uint32_t)buf * TC_TILE, v0);
+                    tmem_ld32(lane_addr + (uint32_t)buf * TC_TILE + 32, v1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.tmem_empty[buf]);      // accumulator buffer may be overwritten
+                    cm[2 * tt] = min32(v0);
+                    cm[2 * tt + 1] = min32(v1);
+                }
+            }
+            // ---- filter: chunks within tau of the row minimum (or of the exact best so far) ----
+            float rmin = cm[0];
+#pragma unroll
+            for (int i = 1; i < 2 * TC_SB_TILES; ++i) rmin = fminf(rmin, cm[i]);
+            S.rowmin[sb & 1][h][row] = rmin;
+            epi_bar();
+            rmin = fminf(rmin, S.rowmin[sb & 1][h ^ 1][row]);
+            float thr = fminf(rmin, best_d * mt.scale2) + mt.tau;
+            if (!(thr == thr)) thr = INFINITY;                       // NaN anywhere: evaluate everything
+            uint32_t mask = 0;
+#pragma unroll
+            for (int i = 0; i < 2 * TC_SB_TILES; ++i) mask |= (cm[i] <= thr || !(cm[i] == cm[i])) ? (1u << i) : 0u;
+            if (!live) mask = 0;
+            // ---- exact float32 re-evaluation of the surviving chunks (reference expression) ----
+            while (mask) {
+                const int i = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int t0 = (sb * TC_SB_TILES + (i >> 1)) * TC_TILE + h * 64 + (i & 1) * 32;
+                const int t1 = min(t0 + 32, nt);
+                for (int t = t0; t < t1; ++t) {
+                    const float* s = Tx + 3 * (size_t)t;
+                    const float d = ref_sqdist_tc(qx, qy, qz, __ldg(s), __ldg(s + 1), __ldg(s + 2));
+                    if (d < best_d || (d == best_d && t < best_i)) { best_d = d; best_i = t; }
+                }
+            }
+        }
+        // ---- merge the two column halves of each row, first minimum wins ----
+        if (h == 1) { S.best_d[row] = best_d; S.best_i[row] = best_i; }
+        epi_bar();
+        if (h == 0 && live) {
+            const float d2 = S.best_d[row]; const int i2 = S.best_i[row];
+            if (d2 < best_d || (d2 == best_d && i2 < best_i)) { best_d = d2; best_i = i2; }
+            dist[gq] = best_d; idx[gq] = best_i;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+    }
+}
+
+// host-side entry used by chamfer.cu -----------------------------------------------------------
+static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+size_t chamfer_tc_workspace_bytes(int B, int n, int m) {
+    const size_t n_pad = round_up(n, TC_TILE), m_pad = round_up(m, TC_TILE);
+    return 2 * (size_t)B * (n_pad + m_pad) * 32 + (((size_t)B * sizeof(ChamferMeta) + 255) & ~(size_t)255) + 256;
+}
+
+int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
+                       float* dist2, int32_t* idx1, int32_t* idx2, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+    if (ws_bytes < chamfer_tc_workspace_bytes(B, n, m) || ws == nullptr)
+        return fail(SPK_E_WORKSPACE, "chamfer_fwd_f32: workspace of %zu bytes needed, %zu given", chamfer_tc_workspace_bytes(B, n, m), ws_bytes);
+    if (((uintptr_t)ws & 15) != 0) return fail(SPK_E_ALIGN, "chamfer_fwd_f32: workspace must be 16-byte aligned");
+    const int n_pad = round_up(n, TC_TILE), m_pad = round_up(m, TC_TILE);
+    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    PrepParams pp;
+    pp.xyz1 = xyz1; pp.xyz2 = xyz2; pp.n = n; pp.m = m; pp.n_pad = n_pad; pp.m_pad = m_pad;
+    pp.meta = reinterpret_cast<ChamferMeta*>(base);
+    unsigned char* ops = base + (((size_t)B * sizeof(ChamferMeta) + 255) & ~(size_t)255);
+    pp.A1 = ops; pp.B1 = pp.A1 + (size_t)B * n_pad * 32;
+    pp.A2 = pp.B1 + (size_t)B * n_pad * 32; pp.B2 = pp.A2 + (size_t)B * m_pad * 32;
+    const int slices = std::max(1, std::min(8, (n_pad + m_pad) / 1024));
+    chamfer_prep_kernel<<<dim3(slices, B), 256, 0, st>>>(pp);
+    SPK_LAUNCH_CHECK("chamfer_prep_kernel");
+
+    TcParams tp;
+    tp.xyz1 = xyz1; tp.xyz2 = xyz2; tp.A1 = pp.A1; tp.B1 = pp.B1; tp.A2 = pp.A2; tp.B2 = pp.B2; tp.meta = pp.meta;
+    tp.dist1 = dist1; tp.dist2 = dist2; tp.idx1 = idx1; tp.idx2 = idx2;
+    tp.n = n; tp.m = m; tp.n_pad = n_pad; tp.m_pad = m_pad;
+    tp.tiles1 = n_pad / TC_TILE; tp.tiles2 = m_pad / TC_TILE;
+    // request enough shared memory that at most 2 CTAs share an SM (each owns 256 of the 512 TMEM columns)
+    const size_t smem = std::max(sizeof(TcSmem) + 128, (size_t)80 * 1024);
+    SPK_CUDA(cudaFuncSetAttribute(chamfer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chamfer_tc_kernel<<<dim3(tp.tiles1 + tp.tiles2, B), TC_THREADS, smem, st>>>(tp);
+    SPK_LAUNCH_CHECK("chamfer_tc_kernel");
+    return SPK_OK;
+}
+
+}  // namespace spk

@@ -2,18 +2,22 @@
 //
 // Replaces the region loop's `torch.sort(..., descending=True)` + `[:, :k]` (reference
 // softpool.py:139-142), the float index cube (softpool.py:136-137,146-147) and the Sorter's
-// argmax (softpool.py:95).  One CTA per (b, r) row; the row lives in shared memory as unique
-// 64-bit words  (order_key(key) << 32) | (0xFFFFFFFF - n)  so that ANY sorting network yields the
-// stable descending order of the reference (ties -> lower n first, NaN first, -0 == +0).
+// argmax (softpool.py:95).  One 256-thread CTA per (b, r) row, 8 CTAs per SM.
 //
-// Algorithm: bitonic top-k.  Sort chunks of K2 = pow2 >= k with alternating direction, then
-// repeatedly keep the element-wise max of chunk pairs (the K2 largest of a bitonic sequence of
-// 2*K2) and re-merge, halving the live length each round.  Work ~ N*(log^2 K2 / 2 + 2 log K2)
-// compare-exchanges instead of N*log^2 N / 2 for the full sort; degenerates to a full bitonic
-// sort when K2 == Npad (the reference operating point k*R == N with R == 1, or k > N/2).
+// Algorithm (select, compact, sort the survivors):
+//   1. keys -> order_key (u32 total order: NaN first, -0 == +0), parked in shared memory;
+//   2. radix select, 2 bits per round (16 rounds, one barrier each): the largest V with
+//      #(key >= V) >= k is the k-th largest key;
+//   3. everything > V is selected, plus the first k - #(key > V) of the keys == V in ascending
+//      index order (block prefix sums) -> the selected SET equals the stable-sort prefix;
+//   4. the k survivors, packed as unique u64 (key << 32 | ~n), are bitonic-sorted descending:
+//      ties come out in ascending n, i.e. the stable descending order of the reference.
+// Work is O(N) + O(k log^2 k) per row instead of the full O(N log^2 N) sort the reference does.
 #include "spk_common.cuh"
 
 namespace spk {
+
+constexpr int TOPK_THREADS = 256;
 
 __device__ __forceinline__ void ce_stage(uint64_t* buf, int len, int size, int stride, int tid,
                                          int nthr) {
@@ -32,44 +36,70 @@ __device__ __forceinline__ void stage_sync(int stride, int prev_stride) {
     if (stride >= 64 || prev_stride >= 64) __syncthreads(); else __syncwarp();
 }
 
-__global__ void __launch_bounds__(1024)
-sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int Npad, int K2,
+// exclusive prefix sum of one int per thread over the 256-thread CTA; returns the grand total
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot /*[8]*/, int tid, int& total) {
+    const int lane = tid & 31, warp = tid >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < TOPK_THREADS / 32; ++w) {
+        const int t = warp_tot[w];
+        if (w < warp) base += t;
+        tot += t;
+    }
+    total = tot;
+    __syncthreads();                     // warp_tot may be reused by the caller
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K2,
                int32_t* __restrict__ idx, float* __restrict__ sp_idx,
                int64_t* __restrict__ id_activa) {
-    extern __shared__ __align__(16) uint64_t buf[];
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);                 // K2 survivors
+    uint32_t* sk = reinterpret_cast<uint32_t*>(sel + K2);                  // E*256 keys, [e][t]
+    __shared__ uint32_t wsum[2][TOPK_THREADS / 32][2];
+    __shared__ int warp_tot[TOPK_THREADS / 32];
+    const int tid = threadIdx.x;
     const int row = blockIdx.x;
     const int b = row / R, r = row - b * R;
     const float* krow = keys + (size_t)row * N;
 
-    // ---- load + pack ----------------------------------------------------------------------
-    if ((N & 3) == 0) {
-        const float4* k4 = reinterpret_cast<const float4*>(krow);
-        for (int q = tid; q < (Npad >> 2); q += nthr) {
-            const int i = q << 2;
-            if (i < N) {
-                const float4 v = __ldg(k4 + q);
-                buf[i + 0] = ((uint64_t)order_key(v.x) << 32) | (uint32_t)(0xFFFFFFFFu - (i + 0));
-                buf[i + 1] = ((uint64_t)order_key(v.y) << 32) | (uint32_t)(0xFFFFFFFFu - (i + 1));
-                buf[i + 2] = ((uint64_t)order_key(v.z) << 32) | (uint32_t)(0xFFFFFFFFu - (i + 2));
-                buf[i + 3] = ((uint64_t)order_key(v.w) << 32) | (uint32_t)(0xFFFFFFFFu - (i + 3));
-            } else {
-                buf[i + 0] = 0ull; buf[i + 1] = 0ull; buf[i + 2] = 0ull; buf[i + 3] = 0ull;
-            }
+    // ---- 1. load: thread t owns the E consecutive points n = t*E .. t*E+E-1 ------------------------
+    const int n0 = tid * E;
+    if ((E & 3) == 0 && (N & 3) == 0) {
+        for (int e = 0; e < E; e += 4) {
+            const int n = n0 + e;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool in = n < N;                                          // N%4==0: all four or none
+            if (in) v = __ldg(reinterpret_cast<const float4*>(krow + n));
+            sk[(e + 0) * TOPK_THREADS + tid] = in ? order_key(v.x) : 0u;   // pad 0 < every real key
+            sk[(e + 1) * TOPK_THREADS + tid] = in ? order_key(v.y) : 0u;
+            sk[(e + 2) * TOPK_THREADS + tid] = in ? order_key(v.z) : 0u;
+            sk[(e + 3) * TOPK_THREADS + tid] = in ? order_key(v.w) : 0u;
         }
-        if (Npad < 4) for (int i = tid; i < Npad; i += nthr) buf[i] = 0ull;  // N%4==0 => N>=4, unreachable
     } else {
-        for (int i = tid; i < Npad; i += nthr)
-            buf[i] = (i < N) ? (((uint64_t)order_key(__ldg(krow + i)) << 32) | (uint32_t)(0xFFFFFFFFu - i))
-                             : 0ull;   // pads sort last: every real word is > 0
+        for (int e = 0; e < E; ++e) {
+            const int n = n0 + e;
+            sk[e * TOPK_THREADS + tid] = (n < N) ? order_key(__ldg(krow + n)) : 0u;
+        }
     }
+    for (int i = tid; i < K2; i += TOPK_THREADS) sel[i] = 0ull;
 
-    // ---- argmax over the R rows for this CTA's slice of n (softpool.py:95) --------------------
+    // ---- argmax over the R rows for this CTA's slice of n (softpool.py:95) --------------------------
     if (id_activa != nullptr) {
         const int slice = (N + R - 1) / R;
-        const int n0 = r * slice, n1 = min(N, n0 + slice);
+        const int s0 = r * slice, s1 = min(N, s0 + slice);
         const float* kb = keys + (size_t)b * R * N;
-        for (int n = n0 + tid; n < n1; n += nthr) {
+        for (int n = s0 + tid; n < s1; n += TOPK_THREADS) {
             uint32_t bestk = order_key(__ldg(kb + n));
             int besti = 0;
             for (int rr = 1; rr < R; ++rr) {
@@ -81,54 +111,71 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int Npad, in
     }
     __syncthreads();
 
-    // ---- sort chunks of K2, directions alternating ---------------------------------------------
+    // ---- 2. radix select of the k-th largest key, 2 bits per round ---------------------------------------
+    uint32_t V = 0;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int round = 0; round < 16; ++round) {
+        const int sh = 30 - 2 * round;
+        const uint32_t T1 = V | (1u << sh), T2 = V | (2u << sh), T3 = V | (3u << sh);
+        uint32_t c12 = 0, c3 = 0;
+#pragma unroll 4
+        for (int e = 0; e < E; ++e) {
+            const uint32_t key = sk[e * TOPK_THREADS + tid];
+            c12 += (key >= T1 ? 1u : 0u) + (key >= T2 ? 0x10000u : 0u);
+            c3 += (key >= T3 ? 1u : 0u);
+        }
+        c12 = __reduce_add_sync(0xFFFFFFFFu, c12);      // per-warp counts <= 32*64 fit 16 bits
+        c3 = __reduce_add_sync(0xFFFFFFFFu, c3);
+        const int buf = round & 1;
+        if (lane == 0) { wsum[buf][warp][0] = c12; wsum[buf][warp][1] = c3; }
+        __syncthreads();
+        uint32_t t12 = 0, t3 = 0;
+#pragma unroll
+        for (int w = 0; w < TOPK_THREADS / 32; ++w) { t12 += wsum[buf][w][0]; t3 += wsum[buf][w][1]; }
+        const uint32_t n1 = t12 & 0xFFFFu, n2 = t12 >> 16;        // totals <= 16384
+        if (t3 >= (uint32_t)k) V = T3; else if (n2 >= (uint32_t)k) V = T2; else if (n1 >= (uint32_t)k) V = T1;
+    }
+
+    // ---- 3. compaction in index order ---------------------------------------------------------------------
+    int my_gt = 0, my_eq = 0;
+#pragma unroll 4
+    for (int e = 0; e < E; ++e) {
+        const uint32_t key = sk[e * TOPK_THREADS + tid];
+        my_gt += key > V; my_eq += key == V;
+    }
+    int total_gt, total_eq;
+    const int eq_before = block_exclusive_scan(my_eq, warp_tot, tid, total_eq);
+    (void)block_exclusive_scan(my_gt, warp_tot, tid, total_gt);
+    const int need = k - total_gt;                       // >= 1 ties to take, lowest indices first
+    const int my_eq_taken = max(0, min(my_eq, need - eq_before));
+    int total_sel;
+    int pos = block_exclusive_scan(my_gt + my_eq_taken, warp_tot, tid, total_sel);
+    int eq_rank = eq_before;
+    for (int e = 0; e < E; ++e) {
+        const uint32_t key = sk[e * TOPK_THREADS + tid];
+        bool take = key > V;
+        if (key == V) { take = eq_rank < need; ++eq_rank; }
+        if (take) { sel[pos++] = ((uint64_t)key << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)(n0 + e)); }
+    }
+
+    // ---- 4. sort the survivors (descending; unique words => stable order) ---------------------------------
     int prev = 64;
     for (int size = 2; size <= K2; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             stage_sync(stride, prev);
-            ce_stage(buf, Npad, size, stride, tid, nthr);
+            ce_stage(sel, K2, size, stride, tid, TOPK_THREADS);
             prev = stride;
         }
-
-    // ---- halve: keep the K2 largest of every chunk pair, re-merge ------------------------------
-    const int lg = __ffs(K2) - 1;
-    for (int len = Npad; len > K2;) {
-        const int half = len >> 1;
-        uint64_t v[8];
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int p = tid + it * nthr;
-            if (p < half) {
-                const int c = p >> lg, i = p & (K2 - 1);
-                const uint64_t a = buf[((2 * c) << lg) + i], d = buf[((2 * c + 1) << lg) + i];
-                v[it] = a > d ? a : d;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int p = tid + it * nthr;
-            if (p < half) buf[p] = v[it];
-        }
-        len = half;
-        prev = 64;
-        for (int stride = K2 >> 1; stride > 0; stride >>= 1) {
-            stage_sync(stride, prev);
-            ce_stage(buf, len, K2, stride, tid, nthr);
-            prev = stride;
-        }
-    }
     __syncthreads();
 
-    // ---- emit -----------------------------------------------------------------------------------
+    // ---- emit ---------------------------------------------------------------------------------------------
     int32_t* orow = idx + (size_t)row * k;
-    for (int j = tid; j < k; j += nthr) orow[j] = (int32_t)(0xFFFFFFFFu - (uint32_t)buf[j]);
+    for (int j = tid; j < k; j += TOPK_THREADS) orow[j] = (int32_t)(0xFFFFFFFFu - (uint32_t)sel[j]);
     if (sp_idx != nullptr) {
         const int Q = R + 3;
-        for (int e = tid; e < Q * k; e += nthr) {
+        for (int e = tid; e < Q * k; e += TOPK_THREADS) {
             const int q = e / k, j = e - q * k;
-            sp_idx[(((size_t)b * Q + q) * R + r) * k + j] = (float)(0xFFFFFFFFu - (uint32_t)buf[j]);
+            sp_idx[(((size_t)b * Q + q) * R + r) * k + j] = (float)(0xFFFFFFFFu - (uint32_t)sel[j]);
         }
     }
 }
@@ -162,12 +209,12 @@ extern "C" int sp_topk_f32(const float* keys, int B, int R, int N, int k, int32_
     if (sp_idx && N >= (1 << 24)) return fail(SPK_E_UNSUPPORTED, "sp_topk_f32: N >= 2^24 not exact in float32");
     if ((N & 3) == 0 && ((uintptr_t)keys & 15)) return fail(SPK_E_ALIGN, "sp_topk_f32: keys must be 16-byte aligned");
     const int K2 = max(2, next_pow2(k));
-    const int Npad = max(K2, next_pow2(N));
-    const int nthr = min(1024, max(32, Npad / 2));
-    const size_t smem = (size_t)Npad * sizeof(uint64_t);
+    int E = (N + TOPK_THREADS - 1) / TOPK_THREADS;
+    if (E > 4) E = (E + 3) & ~3;                       // float4 path wants E % 4 == 0
+    const size_t smem = (size_t)K2 * sizeof(uint64_t) + (size_t)E * TOPK_THREADS * sizeof(uint32_t);
     if (smem > 48 * 1024)
         SPK_CUDA(cudaFuncSetAttribute(sp_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sp_topk_kernel<<<B * R, nthr, smem, (cudaStream_t)stream>>>(keys, R, N, k, Npad, K2, idx, sp_idx, id_activa);
+    sp_topk_kernel<<<B * R, TOPK_THREADS, smem, (cudaStream_t)stream>>>(keys, R, N, k, E, K2, idx, sp_idx, id_activa);
     SPK_LAUNCH_CHECK("sp_topk_kernel");
     return SPK_OK;
 }

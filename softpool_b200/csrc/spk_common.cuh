@@ -31,6 +31,12 @@ int cuda_fail(cudaError_t e, const char* what);
 int sm_count();          // SMs of the current device (cached per device)
 int max_optin_smem();    // cudaDevAttrMaxSharedMemoryPerBlockOptin of the current device
 
+// tensor-core Chamfer forward (chamfer_tc.cu)
+size_t chamfer_tc_workspace_bytes(int B, int n, int m);
+int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
+                       float* dist2, int32_t* idx1, int32_t* idx2, void* ws, size_t ws_bytes,
+                       cudaStream_t st);
+
 static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // ---- total order of float32 keys -------------------------------------------------------------

@@ -81,3 +81,19 @@ def test_torch_port_matches_reference(case):
     assert np.array_equal(bits(sp_cube.numpy()), bits(g["sp_cube"]))
     assert np.array_equal(bits(cabins.numpy()), bits(g["cabins"]))
     np.testing.assert_allclose(grad.numpy(), g["grad_x"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("case", golden_cases("chamfer_ref"))
+def test_chamfer_oracle_matches_reference_kernel_outputs(case):
+    """tests/golden/chamfer_ref_*.npz are outputs of the reference's own chamfer.cu (compiled
+    unmodified for sm_100 into oracle/_ref, run on a B200 by
+    tests/test_chamfer_gpu.py::test_c_oracle_matches_reference_kernel): distances and indices of
+    the C restatement must match them bit for bit, gradients within float32 atomics noise."""
+    from oracle import chamfer_oracle as co
+    g = np.load(os.path.join(GOLDEN, "chamfer_ref_%s.npz" % case))
+    d1, d2, i1, i2 = co.forward(g["xyz1"], g["xyz2"])
+    assert np.array_equal(i1, g["idx1"]) and np.array_equal(i2, g["idx2"])
+    assert np.array_equal(bits(d1), bits(g["dist1"])) and np.array_equal(bits(d2), bits(g["dist2"]))
+    gx1, gx2 = co.backward(g["xyz1"], g["xyz2"], g["g1"], g["g2"], i1, i2)
+    np.testing.assert_allclose(gx1, g["grad_xyz1"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(gx2, g["grad_xyz2"], rtol=1e-4, atol=1e-6)
