@@ -10,18 +10,19 @@
 //     A'(p) = [-2xh,-2xh,-2xl, -2yh,-2yh,-2yl, -2zh,-2zh,-2zl,  nh,nm,nl,  1,1,1,  0]
 //     B'(q) = [  xh,  xl,  xh,   yh,  yl,  yh,   zh,  zl,  zh,   1, 1, 1,  mh,mm,ml, 0]
 // The approximate block only FILTERS: per query row the epilogue keeps the minimum of every
-// 32-target chunk (one 3-input FMNMX3 per two elements -- the whole per-element cost), then only
+// 16-target chunk (one 3-input FMNMX3 per two elements -- the whole per-element cost), then only
 // chunks whose minimum is within tau = 2e of the row minimum are re-evaluated with the reference's
 // exact float32 expression  d = fma(dz,dz, fma(dx,dx, dy*dy))  and first-minimum tie rule.  A chunk
 // that holds the true nearest neighbour always passes the filter (its approximate distance is
 // <= d_true + e <= d_any + e <= approx_any + 2e), so the result equals the brute-force one.
 //
-// Kernel structure (one CTA = 128 queries of one sample and direction, 2 CTAs per SM):
-//   warp 0   TMA producer: A tile (128 x 32 B) once, B tiles (128 targets x 32 B) through a ring
+// Kernel structure (persistent, 2 CTAs per SM; a job = 128 queries of one sample and direction):
+//   warp 0   TMA producer: A tile (128 x 32 B) per job, B tiles (128 targets x 32 B) through a ring,
+//            and the raw float4 coordinates of every 1024-target super-block (for the exact pass)
 //   warp 1   TMEM alloc (256 columns = 2 accumulator buffers of 128) + single-thread tcgen05.mma
 //            issue (M=128, N=128, K=16, kind::f16, fp32 accumulate) + tcgen05.commit -> mbarriers
-//   warps 2-9  epilogue: tcgen05.ld 32x32b.x32 -> chunk minima in registers; every 2048 targets
-//            the filter + exact re-evaluation; final (dist, idx) store
+//   warps 2-9  epilogue: tcgen05.ld 32x32b.x32 -> minima of 16-target chunks in registers; every
+//            1024 targets the filter + exact re-evaluation from shared memory; final store
 // Operands are pre-formatted by chamfer_prep_kernel in the canonical no-swizzle K-major layout
 // (8-row x 16-byte core matrices, LBO = 128 B, SBO = 256 B), so tiles move with 1-D bulk copies.
 #include "spk_common.cuh"
@@ -29,10 +30,14 @@
 
 namespace spk {
 
-constexpr int TC_TILE = 128;            // queries per CTA = targets per MMA tile
+constexpr int TC_TILE = 128;            // queries per CTA = targets per shared-memory B tile
+constexpr int TC_N = 128;               // targets per MMA (accumulator buffer width, TMEM columns)
+constexpr int TC_NBUF = 2;              // accumulator buffers: hides the release -> MMA -> commit round trip
 constexpr int TC_STAGES = 4;            // B-tile ring depth
 constexpr int TC_THREADS = 320;         // 10 warps
-constexpr int TC_SB_TILES = 16;         // tiles per super-block (2048 targets)
+constexpr int TC_SB_TILES = 8;          // tiles per super-block (1024 targets)
+constexpr int TC_SB_TARGETS = TC_SB_TILES * TC_TILE;
+constexpr int TC_CHUNK = 16;            // targets per filter chunk
 constexpr int TC_TILE_BYTES = TC_TILE * 32;
 constexpr float TC_PAD_NORM = 30000.f;  // norm of padding targets: never the minimum
 
@@ -94,6 +99,7 @@ struct PrepParams {
     const float* xyz1; const float* xyz2;
     int n, m, n_pad, m_pad;
     unsigned char* A1; unsigned char* B1; unsigned char* A2; unsigned char* B2;   // per sample n_pad*32 / m_pad*32 bytes
+    float4* T1; float4* T2;          // raw coordinates (x,y,z,0), padded per sample to n_pad / m_pad rows
     ChamferMeta* meta;
 };
 
@@ -163,11 +169,14 @@ chamfer_prep_kernel(const PrepParams p) {
         const int r = first ? i : i - p.n_pad;
         const bool real = r < (first ? p.n : p.m);
         float ux = 0.f, uy = 0.f, uz = 0.f;
+        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
         if (real) {
             const float* s = (first ? P : Q) + 3 * (size_t)r;
-            ux = (__ldg(s) - cx) * sc; uy = (__ldg(s + 1) - cy) * sc; uz = (__ldg(s + 2) - cz) * sc;
+            raw.x = __ldg(s); raw.y = __ldg(s + 1); raw.z = __ldg(s + 2);
+            ux = (raw.x - cx) * sc; uy = (raw.y - cy) * sc; uz = (raw.z - cz) * sc;
         }
         write_rows(first ? A1 : A2, first ? B1 : B2, r, real, ux, uy, uz);
+        (first ? p.T1 + (size_t)b * p.n_pad : p.T2 + (size_t)b * p.m_pad)[r] = raw;
     }
 }
 
@@ -187,8 +196,8 @@ __device__ __forceinline__ uint64_t umma_smem_desc(const void* smem_ptr) {
     d |= (uint64_t)1 << 46;
     return d;
 }
-// kind::f16: A, B = F16 (0), D = F32 (1), both K-major, M = 128, N = 128
-constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::f16: A, B = F16 (0), D = F32 (1), both K-major, M = 128, N = TC_N
+constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
     asm volatile(
@@ -216,6 +225,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float min3(float a, float b, float c) {
     float r;
@@ -241,46 +262,43 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: 
 struct TcParams {
     const float* xyz1; const float* xyz2;
     const unsigned char* A1; const unsigned char* B1; const unsigned char* A2; const unsigned char* B2;
+    const float4* T1; const float4* T2;
     const ChamferMeta* meta;
     float* dist1; float* dist2; int32_t* idx1; int32_t* idx2;
-    int n, m, n_pad, m_pad;
+    int B, n, m, n_pad, m_pad;
     int tiles1, tiles2;      // query tiles per sample in direction 0 / 1
 };
 
 struct __align__(128) TcSmem {
     unsigned char a_tile[TC_TILE_BYTES];
     unsigned char b_tile[TC_STAGES][TC_TILE_BYTES];
-    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full, tmem_full[2], tmem_empty[2];
+    float4 t4[2][TC_SB_TARGETS];                               // raw target coordinates, per super-block
+    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full, a_empty, tmem_full[TC_NBUF], tmem_empty[TC_NBUF], t4_full[2], t4_empty[2];
     uint32_t tmem_base;
     float rowmin[2][2][TC_TILE];          // [super-block parity][column half][row]
     float best_d[TC_TILE]; int best_i[TC_TILE];
 };
+
+__device__ __forceinline__ float min16(const float* v) {
+    float m0 = min3(v[0], v[1], v[2]), m1 = min3(v[3], v[4], v[5]);
+    m0 = min3(m0, v[6], v[7]); m1 = min3(m1, v[8], v[9]);
+    m0 = min3(m0, v[10], v[11]); m1 = min3(m1, v[12], v[13]);
+    return min3(m0, m1, fminf(v[14], v[15]));
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
 chamfer_tc_kernel(const TcParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // which (direction, sample, query tile)
-    int job = blockIdx.x;
-    const int b = blockIdx.y;
-    const int dir = job < p.tiles1 ? 0 : 1;
-    if (dir) job -= p.tiles1;
-    const int nq = dir ? p.m : p.n, nt = dir ? p.n : p.m;
-    const int nq_pad = dir ? p.m_pad : p.n_pad, nt_pad = dir ? p.n_pad : p.m_pad;
-    const float* Qx = (dir ? p.xyz2 : p.xyz1) + (size_t)b * nq * 3;
-    const float* Tx = (dir ? p.xyz1 : p.xyz2) + (size_t)b * nt * 3;
-    const unsigned char* Aop = (dir ? p.A2 : p.A1) + ((size_t)b * nq_pad + (size_t)job * TC_TILE) * 32;
-    const unsigned char* Bop = (dir ? p.B1 : p.B2) + (size_t)b * nt_pad * 32;
-    float* dist = (dir ? p.dist2 : p.dist1) + (size_t)b * nq;
-    int32_t* idx = (dir ? p.idx2 : p.idx1) + (size_t)b * nq;
-    const int T = nt_pad / TC_TILE;                        // target tiles
+    const int jobs_per_sample = p.tiles1 + p.tiles2;
+    const int total_jobs = jobs_per_sample * p.B;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-        mbar_init(&S.a_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], 8); }
+        mbar_init(&S.a_full, 1); mbar_init(&S.a_empty, 1);
+        for (int i = 0; i < TC_NBUF; ++i) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&S.t4_full[i], 1); mbar_init(&S.t4_empty[i], 8); }
         fence_mbar_init();
     }
     if (warp == 1) {   // TMEM: 256 columns (2 x 128-column fp32 accumulators)
@@ -292,103 +310,154 @@ chamfer_tc_kernel(const TcParams p) {
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
 
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            mbar_expect_tx(&S.a_full, TC_TILE_BYTES);
-            bulk_g2s(S.a_tile, Aop, TC_TILE_BYTES, &S.a_full);
-            for (int t = 0; t < T; ++t) {
-                const int s = t % TC_STAGES;
-                mbar_wait(&S.empty[s], (uint32_t)(((t / TC_STAGES) & 1) ^ 1));
-                mbar_expect_tx(&S.full[s], TC_TILE_BYTES);
-                bulk_g2s(S.b_tile[s], Bop + (size_t)t * TC_TILE_BYTES, TC_TILE_BYTES, &S.full[s]);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            mbar_wait(&S.a_full, 0);
-            const uint64_t a_desc = umma_smem_desc(S.a_tile);
-            for (int t = 0; t < T; ++t) {
-                const int s = t % TC_STAGES, buf = t & 1;
-                mbar_wait(&S.tmem_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1));
-                mbar_wait(&S.full[s], (uint32_t)((t / TC_STAGES) & 1));
-                tc_fence_after();
-                umma_f16(tmem_base + (uint32_t)buf * TC_TILE, a_desc, umma_smem_desc(S.b_tile[s]), TC_IDESC);
-                umma_commit(&S.empty[s]);            // smem slot free once the MMA has read it
-                umma_commit(&S.tmem_full[buf]);      // accumulator ready for the epilogue
-            }
-        }
-    } else {
-        // ===== epilogue: 8 warps; warp%4 picks the TMEM lane quarter, (warp-2)/4 the column half =====
-        const int q = warp & 3, h = (warp - 2) >> 2;
-        const int row = q * 32 + lane;                         // query row inside the tile
-        const int gq = job * TC_TILE + row;                    // query index inside the cloud
-        const bool live = gq < nq;
-        const ChamferMeta mt = p.meta[b];
-        float qx = 0.f, qy = 0.f, qz = 0.f;
-        if (live) { qx = __ldg(Qx + 3 * (size_t)gq); qy = __ldg(Qx + 3 * (size_t)gq + 1); qz = __ldg(Qx + 3 * (size_t)gq + 2); }
-        // reference: the first target initialises the running best (`k==0 || d<best`, chamfer.cu:36)
-        float best_d = ref_sqdist_tc(qx, qy, qz, __ldg(Tx), __ldg(Tx + 1), __ldg(Tx + 2));
-        int best_i = 0;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 64;
+    // running counters (identical in every role): B-ring slots, accumulator buffers, super-blocks, jobs
+    uint32_t ring_it = 0, acc_it = 0, sb_it = 0, job_it = 0;
 
-        const int n_sb = (T + TC_SB_TILES - 1) / TC_SB_TILES;
-        for (int sb = 0; sb < n_sb; ++sb) {
-            float cm[2 * TC_SB_TILES];
+    for (int job_id = blockIdx.x; job_id < total_jobs; job_id += gridDim.x, ++job_it) {
+        const int b = job_id / jobs_per_sample;
+        int job = job_id - b * jobs_per_sample;
+        const int dir = job < p.tiles1 ? 0 : 1;
+        if (dir) job -= p.tiles1;
+        const int nq = dir ? p.m : p.n, nt = dir ? p.n : p.m;
+        const int nq_pad = dir ? p.m_pad : p.n_pad, nt_pad = dir ? p.n_pad : p.m_pad;
+        const int T = nt_pad / TC_TILE;                        // target tiles
+        const int n_sb = T / TC_SB_TILES;                      // rows are padded to whole super-blocks
+
+        if (warp == 0) {
+            // ===== TMA producer =====
+            if (lane == 0) {
+                const unsigned char* Aop = (dir ? p.A2 : p.A1) + ((size_t)b * nq_pad + (size_t)job * TC_TILE) * 32;
+                const unsigned char* Bop = (dir ? p.B1 : p.B2) + (size_t)b * nt_pad * 32;
+                const float4* T4 = (dir ? p.T1 : p.T2) + (size_t)b * nt_pad;
+                mbar_wait(&S.a_empty, (uint32_t)((job_it & 1) ^ 1));       // previous job's MMAs have read A
+                mbar_expect_tx(&S.a_full, TC_TILE_BYTES);
+                bulk_g2s(S.a_tile, Aop, TC_TILE_BYTES, &S.a_full);
+                for (int sb = 0; sb < n_sb; ++sb) {
+                    const uint32_t sbi = sb_it + sb, pb = sbi & 1;
+                    constexpr int tiles = TC_SB_TILES;
+                    mbar_wait(&S.t4_empty[pb], (uint32_t)(((sbi >> 1) & 1) ^ 1));
+                    mbar_expect_tx(&S.t4_full[pb], (uint32_t)tiles * TC_TILE * 16u);
+                    bulk_g2s(S.t4[pb], T4 + (size_t)sb * TC_SB_TARGETS, (uint32_t)tiles * TC_TILE * 16u, &S.t4_full[pb]);
+                    for (int tt = 0; tt < tiles; ++tt) {
+                        const uint32_t it = ring_it + sb * TC_SB_TILES + tt, s = it % TC_STAGES;
+                        mbar_wait(&S.empty[s], (uint32_t)(((it / TC_STAGES) & 1) ^ 1));
+                        mbar_expect_tx(&S.full[s], TC_TILE_BYTES);
+                        bulk_g2s(S.b_tile[s], Bop + (size_t)(sb * TC_SB_TILES + tt) * TC_TILE_BYTES, TC_TILE_BYTES, &S.full[s]);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer =====
+            if (lane == 0) {
+                mbar_wait(&S.a_full, (uint32_t)(job_it & 1));
+                const uint64_t a_desc = umma_smem_desc(S.a_tile);
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t it = ring_it + t, s = it % TC_STAGES;
+                    mbar_wait(&S.full[s], (uint32_t)((it / TC_STAGES) & 1));
 #pragma unroll
-            for (int tt = 0; tt < TC_SB_TILES; ++tt) {
-                const int t = sb * TC_SB_TILES + tt;
-                cm[2 * tt] = INFINITY; cm[2 * tt + 1] = INFINITY;
-                if (t < T) {
-                    const int buf = t & 1;
-                    mbar_wait(&S.tmem_full[buf], (uint32_t)((t >> 1) & 1));
+                    for (int half = 0; half < TC_TILE / TC_N; ++half) {     // TC_TILE / TC_N MMAs per 128-target smem tile
+                        const uint32_t ai = acc_it + (TC_TILE / TC_N) * t + half, buf = ai % TC_NBUF;
+                        mbar_wait(&S.tmem_empty[buf], (uint32_t)(((ai / TC_NBUF) & 1) ^ 1));
+                        tc_fence_after();
+                        umma_f16(tmem_base + buf * TC_N, a_desc, umma_smem_desc(S.b_tile[s] + half * (TC_N * 32)), TC_IDESC);
+                        umma_commit(&S.tmem_full[buf]);  // accumulator ready for the epilogue
+                    }
+                    umma_commit(&S.empty[s]);            // smem slot free once both MMAs have read it
+                }
+                umma_commit(&S.a_empty);                 // A tile may be replaced
+            }
+        } else {
+            // ===== epilogue: 8 warps; warp%4 picks the TMEM lane quarter, (warp-2)/4 the column half =====
+            const int q = warp & 3, h = (warp - 2) >> 2;
+            const int row = q * 32 + lane;                         // query row inside the tile
+            const int gq = job * TC_TILE + row;                    // query index inside the cloud
+            const bool live = gq < nq;
+            const float* Qx = (dir ? p.xyz2 : p.xyz1) + (size_t)b * nq * 3;
+            const float* Tx = (dir ? p.xyz1 : p.xyz2) + (size_t)b * nt * 3;
+            const float tau = p.meta[b].tau, scale2 = p.meta[b].scale2;
+            float qx = 0.f, qy = 0.f, qz = 0.f;
+            if (live) { qx = __ldg(Qx + 3 * (size_t)gq); qy = __ldg(Qx + 3 * (size_t)gq + 1); qz = __ldg(Qx + 3 * (size_t)gq + 2); }
+            // reference: the first target initialises the running best (`k==0 || d<best`, chamfer.cu:36)
+            float best_d = ref_sqdist_tc(qx, qy, qz, __ldg(Tx), __ldg(Tx + 1), __ldg(Tx + 2));
+            int best_i = 0;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * (TC_N / 2);
+
+            for (int sb = 0; sb < n_sb; ++sb) {
+                // per thread: TC_N/2 columns of every accumulator = TC_N/32 chunks of 16 targets
+                constexpr int CPA = TC_N / 32;                              // chunks per accumulator per thread
+                constexpr int ACC_PER_SB = TC_SB_TARGETS / TC_N;
+                float cm[CPA * ACC_PER_SB];
+#pragma unroll
+                for (int a = 0; a < ACC_PER_SB; ++a) {
+                    const uint32_t ai = acc_it + (uint32_t)(sb * ACC_PER_SB + a), buf = ai % TC_NBUF;
+                    mbar_wait(&S.tmem_full[buf], (ai / TC_NBUF) & 1);
                     tc_fence_after();
-                    float v0[32], v1[32];
-                    tmem_ld32(lane_addr + (uint32_t)buf * TC_TILE, v0);
-                    tmem_ld32(lane_addr + (uint32_t)buf * TC_TILE + 32, v1);
+                    const uint32_t ta = lane_addr + buf * TC_N;
+                    float va[16], vb[16];
+                    tmem_ld16(ta, va);
+                    tmem_ld16(ta + 16, vb);
                     tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < CPA; c += 2) {
+                        cm[CPA * a + c] = min16(va);
+                        if (c + 2 < CPA) tmem_ld16(ta + 16 * (c + 2), va);
+                        cm[CPA * a + c + 1] = min16(vb);
+                        if (c + 2 < CPA) { tmem_ld16(ta + 16 * (c + 3), vb); tmem_ld_wait(); }
+                    }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.tmem_empty[buf]);      // accumulator buffer may be overwritten
-                    cm[2 * tt] = min32(v0);
-                    cm[2 * tt + 1] = min32(v1);
                 }
-            }
-            // ---- filter: chunks within tau of the row minimum (or of the exact best so far) ----
-            float rmin = cm[0];
+                // ---- filter: chunks within tau of the row minimum (or of the exact best so far) ----
+                constexpr int NCM = CPA * ACC_PER_SB;                       // 32
+                float rmin = min3(cm[0], cm[1], cm[2]);
 #pragma unroll
-            for (int i = 1; i < 2 * TC_SB_TILES; ++i) rmin = fminf(rmin, cm[i]);
-            S.rowmin[sb & 1][h][row] = rmin;
+                for (int i = 3; i + 1 < NCM; i += 2) rmin = min3(rmin, cm[i], cm[i + 1]);
+                rmin = fminf(rmin, cm[NCM - 1]);
+                S.rowmin[sb & 1][h][row] = rmin;
+                epi_bar();
+                rmin = fminf(rmin, S.rowmin[sb & 1][h ^ 1][row]);
+                float thr = fminf(rmin, best_d * scale2) + tau;
+                if (!(thr == thr)) thr = INFINITY;                       // NaN anywhere: evaluate everything
+                uint32_t mask = 0;
+#pragma unroll
+                for (int i = 0; i < NCM; ++i) if (!(cm[i] > thr)) mask |= 1u << i;     // NaN minima pass too
+                if (!live) mask = 0;
+                // ---- exact float32 re-evaluation of the surviving chunks (reference expression) ----
+                const uint32_t sbi = sb_it + sb, pb = sbi & 1;
+                mbar_wait(&S.t4_full[pb], (uint32_t)((sbi >> 1) & 1));
+                const float4* tsm = S.t4[pb];
+                const int sb_base = sb * TC_SB_TARGETS;
+                while (mask) {
+                    const int i = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int l0 = (i / CPA) * TC_N + h * (TC_N / 2) + (i % CPA) * TC_CHUNK;   // inside the super-block
+                    // every chunk starts on a 256-byte boundary: rotate the visiting order by the lane so
+                    // that the 8 lanes of a quarter-warp hit 8 different bank groups (no LDS.128 conflicts)
+#pragma unroll 4
+                    for (int j = 0; j < TC_CHUNK; ++j) {
+                        const int jj = (j + lane) & (TC_CHUNK - 1);
+                        const float4 tg = tsm[l0 + jj];
+                        const float d = ref_sqdist_tc(qx, qy, qz, tg.x, tg.y, tg.z);
+                        const int t = sb_base + l0 + jj;
+                        // first minimum: smaller distance, or equal distance at a lower index
+                        if ((d < best_d || (d == best_d && t < best_i)) && t < nt) { best_d = d; best_i = t; }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.t4_empty[pb]);
+            }
+            // ---- merge the two column halves of each row, first minimum wins ----
+            if (h == 1) { S.best_d[row] = best_d; S.best_i[row] = best_i; }
             epi_bar();
-            rmin = fminf(rmin, S.rowmin[sb & 1][h ^ 1][row]);
-            float thr = fminf(rmin, best_d * mt.scale2) + mt.tau;
-            if (!(thr == thr)) thr = INFINITY;                       // NaN anywhere: evaluate everything
-            uint32_t mask = 0;
-#pragma unroll
-            for (int i = 0; i < 2 * TC_SB_TILES; ++i) mask |= (cm[i] <= thr || !(cm[i] == cm[i])) ? (1u << i) : 0u;
-            if (!live) mask = 0;
-            // ---- exact float32 re-evaluation of the surviving chunks (reference expression) ----
-            while (mask) {
-                const int i = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int t0 = (sb * TC_SB_TILES + (i >> 1)) * TC_TILE + h * 64 + (i & 1) * 32;
-                const int t1 = min(t0 + 32, nt);
-                for (int t = t0; t < t1; ++t) {
-                    const float* s = Tx + 3 * (size_t)t;
-                    const float d = ref_sqdist_tc(qx, qy, qz, __ldg(s), __ldg(s + 1), __ldg(s + 2));
-                    if (d < best_d || (d == best_d && t < best_i)) { best_d = d; best_i = t; }
-                }
+            if (h == 0 && live) {
+                const float d2 = S.best_d[row]; const int i2 = S.best_i[row];
+                if (d2 < best_d || (d2 == best_d && i2 < best_i)) { best_d = d2; best_i = i2; }
+                ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = best_d;
+                ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = best_i;
             }
         }
-        // ---- merge the two column halves of each row, first minimum wins ----
-        if (h == 1) { S.best_d[row] = best_d; S.best_i[row] = best_i; }
-        epi_bar();
-        if (h == 0 && live) {
-            const float d2 = S.best_d[row]; const int i2 = S.best_i[row];
-            if (d2 < best_d || (d2 == best_d && i2 < best_i)) { best_d = d2; best_i = i2; }
-            dist[gq] = best_d; idx[gq] = best_i;
-        }
+        ring_it += (uint32_t)T; acc_it += (uint32_t)(TC_TILE / TC_N) * (uint32_t)T; sb_it += (uint32_t)n_sb;
     }
 
     tc_fence_before();
@@ -403,8 +472,9 @@ chamfer_tc_kernel(const TcParams p) {
 static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
 size_t chamfer_tc_workspace_bytes(int B, int n, int m) {
-    const size_t n_pad = round_up(n, TC_TILE), m_pad = round_up(m, TC_TILE);
-    return 2 * (size_t)B * (n_pad + m_pad) * 32 + (((size_t)B * sizeof(ChamferMeta) + 255) & ~(size_t)255) + 256;
+    const size_t n_pad = round_up(n, TC_SB_TARGETS), m_pad = round_up(m, TC_SB_TARGETS);
+    return 2 * (size_t)B * (n_pad + m_pad) * 32 + (size_t)B * (n_pad + m_pad) * 16 +
+           (((size_t)B * sizeof(ChamferMeta) + 255) & ~(size_t)255) + 256;
 }
 
 int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
@@ -413,7 +483,8 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
     if (ws_bytes < chamfer_tc_workspace_bytes(B, n, m) || ws == nullptr)
         return fail(SPK_E_WORKSPACE, "chamfer_fwd_f32: workspace of %zu bytes needed, %zu given", chamfer_tc_workspace_bytes(B, n, m), ws_bytes);
     if (((uintptr_t)ws & 15) != 0) return fail(SPK_E_ALIGN, "chamfer_fwd_f32: workspace must be 16-byte aligned");
-    const int n_pad = round_up(n, TC_TILE), m_pad = round_up(m, TC_TILE);
+    // rows are padded to whole super-blocks so that the target loop has no ragged tail
+    const int n_pad = round_up(n, TC_SB_TARGETS), m_pad = round_up(m, TC_SB_TARGETS);
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     PrepParams pp;
     pp.xyz1 = xyz1; pp.xyz2 = xyz2; pp.n = n; pp.m = m; pp.n_pad = n_pad; pp.m_pad = m_pad;
@@ -421,19 +492,22 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
     unsigned char* ops = base + (((size_t)B * sizeof(ChamferMeta) + 255) & ~(size_t)255);
     pp.A1 = ops; pp.B1 = pp.A1 + (size_t)B * n_pad * 32;
     pp.A2 = pp.B1 + (size_t)B * n_pad * 32; pp.B2 = pp.A2 + (size_t)B * m_pad * 32;
+    pp.T1 = reinterpret_cast<float4*>(pp.B2 + (size_t)B * m_pad * 32); pp.T2 = pp.T1 + (size_t)B * n_pad;
     const int slices = std::max(1, std::min(8, (n_pad + m_pad) / 1024));
     chamfer_prep_kernel<<<dim3(slices, B), 256, 0, st>>>(pp);
     SPK_LAUNCH_CHECK("chamfer_prep_kernel");
 
     TcParams tp;
-    tp.xyz1 = xyz1; tp.xyz2 = xyz2; tp.A1 = pp.A1; tp.B1 = pp.B1; tp.A2 = pp.A2; tp.B2 = pp.B2; tp.meta = pp.meta;
+    tp.xyz1 = xyz1; tp.xyz2 = xyz2; tp.A1 = pp.A1; tp.B1 = pp.B1; tp.A2 = pp.A2; tp.B2 = pp.B2; tp.T1 = pp.T1; tp.T2 = pp.T2; tp.meta = pp.meta; tp.B = B;
     tp.dist1 = dist1; tp.dist2 = dist2; tp.idx1 = idx1; tp.idx2 = idx2;
     tp.n = n; tp.m = m; tp.n_pad = n_pad; tp.m_pad = m_pad;
-    tp.tiles1 = n_pad / TC_TILE; tp.tiles2 = m_pad / TC_TILE;
+    tp.tiles1 = (n + TC_TILE - 1) / TC_TILE; tp.tiles2 = (m + TC_TILE - 1) / TC_TILE;
     // request enough shared memory that at most 2 CTAs share an SM (each owns 256 of the 512 TMEM columns)
     const size_t smem = std::max(sizeof(TcSmem) + 128, (size_t)80 * 1024);
     SPK_CUDA(cudaFuncSetAttribute(chamfer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chamfer_tc_kernel<<<dim3(tp.tiles1 + tp.tiles2, B), TC_THREADS, smem, st>>>(tp);
+    const long long jobs = (long long)(tp.tiles1 + tp.tiles2) * B;
+    const int grid = (int)std::min<long long>(jobs, 2LL * sm_count());         // persistent: 2 CTAs per SM
+    chamfer_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tp);
     SPK_LAUNCH_CHECK("chamfer_tc_kernel");
     return SPK_OK;
 }
