@@ -190,6 +190,7 @@ struct GatherBwdParams {
     int bulk_out;     // N%4==0 and grad_x 16B aligned -> rows leave with cp.async.bulk
     int bulk_in;      // (R*k)%4==0 and g_cube 16B aligned -> g rows arrive with cp.async.bulk
     int nbuf;         // 2 = double-buffered acc/g (default), 1 = single (rows too large for two)
+    int g_direct;     // 1 = upstream gradient read straight from global (R*k too large to stage)
 };
 
 // Each CTA owns a contiguous range of global rows and walks it in groups of <= T rows that lie in
@@ -206,7 +207,7 @@ sp_gather_bwd_kernel(const GatherBwdParams p) {
     uint16_t* idx_s = reinterpret_cast<uint16_t*>(smem_raw + 128);               // RK
     float* gbuf = reinterpret_cast<float*>(smem_raw + 128 + ((RK * 2 + 127) & ~127));   // 2 * T*RK
     const int nbuf = p.nbuf;
-    float* acc = gbuf + (size_t)nbuf * T * RK;                                   // nbuf * T*N
+    float* acc = gbuf + (p.g_direct ? 0 : (size_t)nbuf * T * RK);                // nbuf * T*N
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
     __syncthreads();
 
@@ -224,7 +225,7 @@ sp_gather_bwd_kernel(const GatherBwdParams p) {
         return (int)r;
     };
     auto issue_load = [&](long long g, int rows, int buf) {        // tid 0 only
-        if (p.bulk_in) {
+        if (p.bulk_in && !p.g_direct) {
             const uint32_t bytes = (uint32_t)rows * RK * 4u;
             mbar_expect_tx(&bars[buf], bytes);
             bulk_g2s(gbuf + (size_t)buf * T * RK, p.g_cube + (size_t)g * RK, bytes, &bars[buf]);
@@ -259,7 +260,9 @@ sp_gather_bwd_kernel(const GatherBwdParams p) {
             for (int i = tid; i < n4; i += nthr) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int i = (n4 << 2) + tid; i < rows * N; i += nthr) ac[i] = 0.f;
         }
-        if (p.bulk_in) {
+        if (p.g_direct) {
+            // nothing staged
+        } else if (p.bulk_in) {
             mbar_wait(&bars[buf], (uint32_t)((nbuf == 2 ? (gi >> 1) : gi) & 1));
         } else {
             const float* src = p.g_cube + (size_t)g * RK;
@@ -267,7 +270,7 @@ sp_gather_bwd_kernel(const GatherBwdParams p) {
         }
         __syncthreads();
         // fold the window-max gradient into the slot that won each window (unique slots)
-        if (p.g_cabins != nullptr) {
+        if (p.g_cabins != nullptr && !p.g_direct) {
             for (int e = tid; e < rows * wins; e += nthr) {
                 const int t = e / wins, rw = e - t * wins;
                 const int r = rw / p.cab, w = rw - r * p.cab;
@@ -282,7 +285,20 @@ sp_gather_bwd_kernel(const GatherBwdParams p) {
         for (int r = 0; r < R; ++r) {
             for (int e = tid; e < per_region; e += nthr) {
                 const int t = e / k, j = e - t * k;
-                ac[t * N + idx_s[r * k + j]] += gs[t * RK + r * k + j];
+                float gv;
+                if (!p.g_direct) {
+                    gv = gs[t * RK + r * k + j];
+                } else {
+                    gv = __ldg(p.g_cube + (size_t)(g + t) * RK + (size_t)r * k + j);
+                    if (p.g_cabins != nullptr) {
+                        const int w = j / wl;
+                        if (w < p.cab) {
+                            const size_t o = (size_t)(g + t) * wins + r * p.cab + w;
+                            if ((int)__ldg(p.cab_arg + o) == j - w * wl) gv += __ldg(p.g_cabins + o);
+                        }
+                    }
+                }
+                ac[t * N + idx_s[r * k + j]] += gv;
             }
             __syncthreads();
         }
@@ -393,8 +409,9 @@ extern "C" int sp_gather_bwd_f32(const float* g_cube, const float* g_cabins, con
     const size_t budget = (size_t)max_optin_smem();
     const size_t fixed = 128 + (((size_t)RK * 2 + 127) & ~(size_t)127);
     size_t per_T = 2 * ((size_t)N + (size_t)RK) * 4;                // double-buffered acc + g per row
-    p.nbuf = 2;
+    p.nbuf = 2; p.g_direct = 0;
     if (fixed + per_T > budget) { per_T /= 2; p.nbuf = 1; }
+    if (fixed + per_T > budget) { per_T = (size_t)N * 4; p.g_direct = 1; }
     if (fixed + per_T > budget)
         return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: N=%d, R*k=%lld do not fit shared memory", N, RK);
     // T rows per group: aim at ~72 KB per CTA (3 CTAs per SM)

@@ -83,3 +83,27 @@ def test_module_parameter_layout_matches_reference():
     assert "softpool.sorter.conv1d.weight" in keys and f.sp_points == 256
     with pytest.raises(ValueError):
         spb.SoftPool(cabins=4)
+
+
+def test_dropin_import_names():
+    """`import softpool as sp`, `import dist_chamfer as cd`, `from extensions.chamfer_dist import ...`
+    (reference model.py:12, train.py:18-19, GRNet test.py:19) resolve to this package via dropin/."""
+    import importlib
+    import sys
+    d = os.path.join(ROOT, "dropin")
+    sys.path.insert(0, d)
+    try:
+        for name in ("softpool", "dist_chamfer", "extensions.chamfer_dist"):
+            sys.modules.pop(name, None)
+        sp = importlib.import_module("softpool")
+        cd = importlib.import_module("dist_chamfer")
+        ext = importlib.import_module("extensions.chamfer_dist")
+        assert sp.__file__.startswith(d)
+        for n in ("SoftPool", "SoftPoolFeat", "Sorter", "train2cabins", "Periodics"):
+            assert hasattr(sp, n)
+        assert hasattr(cd, "chamferDist") and hasattr(cd, "chamferFunction")
+        assert hasattr(ext, "ChamferDistance") and hasattr(ext, "ChamferFunction")
+    finally:
+        sys.path.remove(d)
+        for name in ("softpool", "dist_chamfer", "extensions.chamfer_dist", "extensions"):
+            sys.modules.pop(name, None)

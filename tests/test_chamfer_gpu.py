@@ -166,3 +166,82 @@ def test_c_oracle_matches_reference_kernel():
                                 dist1=dist1.cpu().numpy(), dist2=dist2.cpu().numpy(),
                                 idx1=idx1.cpu().numpy(), idx2=idx2.cpu().numpy(), g1=g1, g2=g2,
                                 grad_xyz1=gx1.cpu().numpy(), grad_xyz2=gx2.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core path (chamfer_tc.cu): its fp16-split distance block only FILTERS candidates; every
+# case below is built to stress that filter (near-ties at and below its error budget, poor
+# conditioning, exact duplicates across chunk / half / super-block boundaries)
+# ---------------------------------------------------------------------------------------------
+def _check_exact(a, b):
+    r = co.forward(a, b)
+    o = cuda_forward(a, b)
+    for x, y, name in zip(o, r, ("dist1", "dist2", "idx1", "idx2")):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), name
+    return r
+
+
+@pytest.mark.parametrize("jitter", [0.0, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4])
+def test_tensor_path_lattice_near_ties(jitter):
+    """Targets on a 12^3 lattice, queries at cell centres (+ jitter): 8 corners at (near-)equal distance."""
+    rng = np.random.default_rng(42)
+    g = (np.arange(12, dtype=np.float32) / 12.0 - 0.5)
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)            # 1728 targets
+    b = np.stack([lat[rng.permutation(len(lat))] for _ in range(3)]).astype(np.float32)
+    cells = lat[rng.integers(0, len(lat), size=(3, 1500))] + np.float32(0.5 / 12.0)
+    a = (cells + rng.standard_normal(cells.shape) * jitter).astype(np.float32)
+    r = _check_exact(a, b)
+    if jitter == 0.0:
+        # every query really has several exact minima: the lowest index must have been returned
+        d = ((a[0, :64, None, :] - b[0, None, :, :]) ** 2).sum(-1)
+        assert ((d <= d.min(1, keepdims=True) * (1 + 1e-6)).sum(1) >= 2).all()
+
+
+@pytest.mark.parametrize("offset,spread", [(1000.0, 1.0), (1000.0, 1e-3), (-3e4, 10.0), (0.0, 1e-6), (5.0, 5e4)])
+def test_tensor_path_poor_conditioning(offset, spread):
+    """Clouds far from the origin / tiny / huge: the approximate block degrades, the result may not."""
+    rng = np.random.default_rng(7)
+    a = (offset + spread * (rng.random((2, 600, 3)) - 0.5)).astype(np.float32)
+    b = (offset + spread * (rng.random((2, 1300, 3)) - 0.5)).astype(np.float32)
+    _check_exact(a, b)
+
+
+def test_tensor_path_duplicates_across_boundaries():
+    """Exact duplicates 16, 64, 128, 1024 and 2048 targets apart (chunk, column half, tile, super-block):
+    the FIRST one wins; also clustered data with far outliers."""
+    rng = np.random.default_rng(9)
+    b = (rng.random((2, 4096, 3), dtype=np.float32) - 0.5)
+    for gap in (16, 64, 128, 1024, 2048):
+        b[:, gap:gap + 8] = b[:, 0:8]
+    b[:, 3000] = b[:, 5]
+    a = b[:, rng.integers(0, 4096, size=1000)] + np.float32(0.0)
+    a[:, :8] = b[:, 0:8]
+    r = _check_exact(a, b)
+    assert (r[2][:, :8] == np.arange(8)).all() and (r[0][:, :8] == 0).all()
+    c = (rng.standard_normal((2, 2000, 3)) * 0.01).astype(np.float32)
+    c[:, ::97] += 50.0
+    _check_exact(c, (c[:, ::-1] * np.float32(1.0000001)).astype(np.float32).copy())
+
+
+def test_tensor_and_fma_paths_agree(monkeypatch):
+    """The A/B switch: SPK_CHAMFER_EXACT=1 forces the plain float32 FMA kernel; both paths are bit-identical."""
+    from softpool_b200 import _lib
+    assert _lib.lib().chamfer_fwd_workspace_bytes(4, 2048, 2048) > 0
+    a, b = clouds(4, 2048, 3000, seed=77)
+    tc = cuda_forward(a, b)
+    monkeypatch.setenv("SPK_CHAMFER_EXACT", "1")
+    fma = cuda_forward(a, b)
+    for x, y in zip(tc, fma):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
+def test_non_finite_inputs_do_not_hang():
+    a, b = clouds(2, 400, 700, seed=5)
+    a[0, 3] = np.nan
+    b[1, 10, 1] = np.inf
+    b[0, 0] = np.nan                       # the first target initialises the running best
+    d1, d2, i1, i2 = cuda_forward(a, b)
+    assert i1.min() >= 0 and i1.max() < 700 and i2.min() >= 0 and i2.max() < 400
+    ok = np.ones(400, bool); ok[3] = False
+    r = co.forward(a[1:], b[1:])           # sample 1 has an inf coordinate but no NaN: still comparable
+    assert np.array_equal(i1[1], r[2][0])
