@@ -217,26 +217,26 @@ def run_b200(args, w, rank, local_rank, world):
     points_per_step = spd.sum_over_ranks(B * N, dev)
     value = points_per_step / (ms_per_step * 1e-3) / 1e6
 
-    # ---- instrumented pass: per-kernel CUDA-event times, L2 flushed before every step --------------
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-    n_inst = max(10, min(args.steps, 50))
-    per = {k: [] for k in KERNELS}
+    # ---- per-kernel device time: every C-ABI call captured alone in a CUDA graph (30 launches rotating
+    # over the buffer sets, so its inputs are not L2-resident), CUDA events around 5 replays on `stream`
+    kern_us = {}
     with torch.cuda.stream(stream):
-        evs = []
-        for i in range(n_inst):
-            s = sets[i % nsets]
-            flush.zero_(); flush.add_(1.0)                         # evict L2 and let the CPU run ahead
-            row = [torch.cuda.Event(enable_timing=True)]
-            row[0].record(stream)
-            for name, f in step.calls(s):
-                f()
-                ev = torch.cuda.Event(enable_timing=True); ev.record(stream); row.append(ev)
-            evs.append(row)
-        stream.synchronize()
-    for row in evs[2:]:
+        all_calls = [step.calls(s) for s in sets]
+        reps = 10 * nsets
         for j, name in enumerate(KERNELS):
-            per[name].append(row[j].elapsed_time(row[j + 1]) * 1e3)          # us
-    kern_us = {k: statistics.median(v) for k, v in per.items()}
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(reps):
+                    all_calls[i % nsets][j][1]()
+            g.replay()
+            stream.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(stream)
+            for _ in range(5):
+                g.replay()
+            k1.record(stream)
+            stream.synchronize()
+            kern_us[name] = k0.elapsed_time(k1) * 1e3 / (5 * reps)
     fwd_b, bwd_b = algorithmic_bytes(w)
     P = B * N * N
     sp_us = kern_us["sp_topk_f32"] + kern_us["sp_gather_fwd_f32"] + kern_us["sp_gather_bwd_f32"]
@@ -269,7 +269,7 @@ def run_b200(args, w, rank, local_rank, world):
                        "wall_ms_per_step": wall_ms / args.steps, "parallelism": "batch-sharded, no data-path collective"},
             "roofline": dominant, "roofline_softpool": roof_sp, "roofline_chamfer": roof_ch,
             "kernel_us": kern_us, "softpool_fwd_bwd_us": sp_us, "chamfer_fwd_bwd_us": ch_us,
-            "kernel_timing": "median of %d instrumented steps, CUDA events between launches, 256 MB L2 flush before each step" % (n_inst - 2),
+            "kernel_timing": "per C-ABI call: CUDA events around 5 replays of a CUDA graph holding %d launches that rotate over the %d buffer sets" % (reps, nsets),
             "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "clocks": clocks,
         }
     return out

@@ -1,27 +1,52 @@
-// softpool_gather.cu -- SoftPool gather forward (+ window max) and its scatter-free backward.
+// softpool_gather.cu -- SoftPool gather forward (+ window max) and its atomic-free backward.
 //
 // Forward replaces softpool.py:142-145 + train2cabins (softpool.py:71-85); backward is what
 // autograd derives for them (the reference has no hand-written backward).  Both are pure data
 // movement and HBM-bound; design ("gather"):
-//   * x rows (N floats, contiguous) are streamed into shared memory with 1-D TMA bulk copies
-//     (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP), 2 stages per team, so the random
-//     index access hits shared memory, never HBM/L2; every x byte is read exactly once;
-//   * persistent grid (CTAs = resident slots), every team owns a contiguous, balanced range of
-//     the B*C rows: one wave, no tail;
-//   * outputs leave as 128-bit coalesced stores (forward) / TMA bulk stores of whole grad_x
-//     rows (backward); grad_x is accumulated in shared memory in ascending region order, so it
-//     is deterministic and needs neither atomics nor a pre-zeroed output.
+//   * persistent grid (CTAs = resident slots); every CTA owns a contiguous, balanced range of the
+//     B*C rows and walks it in TILES of T rows of one sample (one index list serves a tile);
+//   * forward: a tile of x (T*N floats, contiguous) arrives in shared memory by ONE 1-D TMA bulk
+//     copy (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP), double-buffered, so the random
+//     index access hits shared memory, never HBM/L2, and every x byte is read exactly once; the
+//     sample's index list sits in shared memory as u16; outputs leave as 128-bit streaming stores;
+//   * backward: per sample the CTA orders the R*k slots by rank (number of lower regions that chose
+//     the same point); slots of one rank hit different points, so a rank bucket is scattered into
+//     a T x N shared-memory accumulator without conflicts or atomics, buckets in ascending rank
+//     (= ascending region: deterministic order); the T finished rows leave with one TMA bulk store
+//     (cp.async.bulk.global.shared::cta) while the next tile is accumulated in the other buffer.
+//     grad_x is fully overwritten (zeros included): no memset.
 #include "spk_common.cuh"
 
 namespace spk {
 
-__device__ __forceinline__ void team_sync(int team_id, int team_threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(team_id + 1), "r"(team_threads) : "memory");
-}
+constexpr int G_THREADS = 256;
 
-// (key, off) max with torch.max tie rule: greater key wins, equal keys -> lower off.
-__device__ __forceinline__ void amax_merge(uint32_t& key, uint32_t& off, uint32_t k2, uint32_t o2) {
-    if (k2 > key || (k2 == key && o2 < off)) { key = k2; off = o2; }
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// contiguous range of global rows of CTA `cta`
+__device__ __forceinline__ void cta_range(long long rows, long long& lo, long long& hi) {
+    lo = (long long)((unsigned long long)rows * blockIdx.x / gridDim.x);
+    hi = (long long)((unsigned long long)rows * (blockIdx.x + 1) / gridDim.x);
+}
+// rows of the tile starting at global row g: <= T, inside the CTA range, inside one sample
+__device__ __forceinline__ int tile_rows(long long g, long long g_hi, int T, int C) {
+    // the host guarantees B*C < 2^31: 32-bit modulo instead of the emulated 64-bit one
+    const unsigned in_sample = (unsigned)C - (unsigned)g % (unsigned)C;
+    long long r = g_hi - g;
+    if (r > T) r = T;
+    if (r > (long long)in_sample) r = in_sample;
+    return (int)r;
+}
+// cooperative load of one sample's index list into shared memory as u16 (4 independent loads in flight)
+__device__ __forceinline__ void stage_idx_u16(const int32_t* __restrict__ src, uint16_t* dst, int n, int tid) {
+    int i = tid;
+    for (; i + 3 * G_THREADS < n; i += 4 * G_THREADS) {
+        const int a = __ldg(src + i), b = __ldg(src + i + G_THREADS), c = __ldg(src + i + 2 * G_THREADS),
+                  d = __ldg(src + i + 3 * G_THREADS);
+        dst[i] = (uint16_t)a; dst[i + G_THREADS] = (uint16_t)b; dst[i + 2 * G_THREADS] = (uint16_t)c;
+        dst[i + 3 * G_THREADS] = (uint16_t)d;
+    }
+    for (; i < n; i += G_THREADS) dst[i] = (uint16_t)__ldg(src + i);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -32,110 +57,119 @@ struct GatherFwdParams {
     float* sp_cube; float* cabins; uint16_t* cab_arg;
     long long rows;       // B*C
     int C, N, R, k, cab;
-    int team_threads;     // 32 (warp per row) or blockDim.x (CTA per row)
-    int stages;           // ring depth per team
-    int bulk_ok;          // rows can move with cp.async.bulk (N%4==0, x 16B aligned)
-    int vec4;             // k%4==0 && sp_cube, idx 16B aligned
-    int cab_fast;         // windows are whole groups of 4 slots, (wl/4) pow2 <= 32
+    int T;                // rows per tile
+    int bulk_ok;          // tiles can move with cp.async.bulk (N%4==0, x 16B aligned)
+    int vec4;             // k%4==0 && sp_cube 16B aligned: 4 slots per work item, 128-bit stores
+    int cab_fast;         // windows are whole groups of 4 slots, (wl/4) pow2 <= 32, (R*k/4) % 32 == 0 if > 1
+    int g_shift;          // log2(wl/4) when cab_fast
+    int q_shift;          // log2(R*k/4) when that is a power of two, else -1
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(G_THREADS)
 sp_gather_fwd_kernel(const GatherFwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    const int team_threads = p.team_threads;
-    const int n_teams = blockDim.x / team_threads;
-    const int team = tid / team_threads, tt = tid - team * team_threads;
-    const int RK = p.R * p.k;
-    const int N = p.N;
-
-    // smem carve-up: [mbarriers][rows: n_teams * stages * N floats]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-    const int n_bars = n_teams * p.stages;
-    float* rows_s = reinterpret_cast<float*>(smem_raw + ((n_bars * 8 + 127) & ~127));
-    float* my_rows = rows_s + (size_t)team * p.stages * N;
-    uint64_t* my_bars = bars + team * p.stages;
-
-    if (tid == 0) {
-        for (int i = 0; i < n_bars; ++i) mbar_init(&bars[i], 1);
-        fence_mbar_init();
-    }
+    const int RK = p.R * p.k, N = p.N, T = p.T, C = p.C;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                            // 2
+    uint16_t* idx_s = reinterpret_cast<uint16_t*>(smem_raw + 128);                     // RK
+    float* tiles = reinterpret_cast<float*>(smem_raw + 128 + ((RK * 2 + 127) & ~127)); // 2 * T*N
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
     __syncthreads();
 
-    // this team's contiguous range of global rows g = b*C + c
-    const long long total_teams = (long long)gridDim.x * n_teams;
-    const long long gteam = (long long)blockIdx.x * n_teams + team;
-    const long long g_lo = p.rows * gteam / total_teams;
-    const long long g_hi = p.rows * (gteam + 1) / total_teams;
-    const int my_count = (int)(g_hi - g_lo);
-
-    if (p.bulk_ok && tt == 0) {
-        for (int s = 0; s < p.stages && s < my_count; ++s) {
-            mbar_expect_tx(&my_bars[s], (uint32_t)N * 4u);
-            bulk_g2s(my_rows + (size_t)s * N, p.x + (size_t)(g_lo + s) * N, (uint32_t)N * 4u, &my_bars[s]);
+    long long g_lo, g_hi;
+    cta_range(p.rows, g_lo, g_hi);
+    auto issue = [&](long long g, int rows, int buf) {             // tid 0 only
+        if (p.bulk_ok) {
+            const uint32_t bytes = (uint32_t)rows * (uint32_t)N * 4u;
+            mbar_expect_tx(&bars[buf], bytes);
+            bulk_g2s(tiles + (size_t)buf * T * N, p.x + (size_t)g * N, bytes, &bars[buf]);
         }
+    };
+    // prologue: two tiles in flight
+    long long g = g_lo, g_pref = g_lo;
+    if (tid == 0) {
+        for (int i = 0; i < 2 && g_pref < g_hi; ++i) { const int r = tile_rows(g_pref, g_hi, T, C); issue(g_pref, r, i); g_pref += r; }
+    } else {
+        for (int i = 0; i < 2 && g_pref < g_hi; ++i) g_pref += tile_rows(g_pref, g_hi, T, C);
     }
 
     const int wl = p.cab > 0 ? p.k / p.cab : 0;          // window length
-    const int G = p.cab_fast ? (wl >> 2) : 1;            // groups (lanes) per window
+    const int G = p.cab_fast ? (wl >> 2) : 1;            // work items (lanes) per window
     const int wins_per_row = p.R * p.cab;
+    const int Q = RK >> 2;                               // 4-slot work items per row
+    int cur_b = -1;
 
-    for (int it = 0; it < my_count; ++it) {
-        const long long g = g_lo + it;
-        const int b = (int)(g / p.C);
-        const int32_t* ib = p.idx + (size_t)b * RK;       // L1/L2-resident: shared by the C rows of b
-        const int s = it % p.stages;
-        float* row = my_rows + (size_t)s * N;
+    for (int ti = 0; g < g_hi; ++ti) {
+        const int buf = ti & 1;
+        const int rows = tile_rows(g, g_hi, T, C);
+        const int b = (int)((unsigned)g / (unsigned)C);
+        if (b != cur_b) {                                // new sample: its index list (readers of the old one
+            stage_idx_u16(p.idx + (size_t)b * RK, idx_s, RK, tid);      // passed the barrier ending the last tile)
+            cur_b = b;
+            __syncthreads();
+        }
+        float* tile = tiles + (size_t)buf * T * N;
         if (p.bulk_ok) {
-            mbar_wait(&my_bars[s], (uint32_t)((it / p.stages) & 1));
+            mbar_wait(&bars[buf], (uint32_t)((ti >> 1) & 1));
         } else {
             const float* src = p.x + (size_t)g * N;
-            for (int i = tt; i < N; i += team_threads) row[i] = __ldg(src + i);
-            team_sync(team, team_threads);
+            for (int i = tid; i < rows * N; i += G_THREADS) tile[i] = __ldg(src + i);
+            __syncthreads();
         }
-        float* orow = p.sp_cube + (size_t)g * RK;
         if (p.vec4) {
-            const int groups = RK >> 2;
-            // loop bound rounded up so that every lane of a window's G-group takes part in shuffles
-            const int groups_up = (groups + team_threads - 1) / team_threads * team_threads;
-            for (int q = tt; q < groups_up; q += team_threads) {
-                const bool live = q < groups;
+            const int items = rows * Q;
+            const int items_up = (items + G_THREADS - 1) / G_THREADS * G_THREADS;     // whole warps reach the shuffles
+            for (int e = tid; e < items_up; e += G_THREADS) {
+                const bool live = e < items;
+                int t, q;
+                if (p.q_shift >= 0) { t = e >> p.q_shift; q = e & (Q - 1); } else { t = e / Q; q = e - t * Q; }
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                int4 iv = make_int4(0, 0, 0, 0);
+                const float* row = tile + (size_t)t * N;
                 if (live) {
-                    iv = __ldg(reinterpret_cast<const int4*>(ib) + q);
-                    v.x = row[iv.x]; v.y = row[iv.y]; v.z = row[iv.z]; v.w = row[iv.w];
-                    st_cs_f4(reinterpret_cast<float4*>(orow) + q, v);
+                    const uint2 u = *reinterpret_cast<const uint2*>(idx_s + 4 * q);
+                    v.x = row[u.x & 0xFFFFu]; v.y = row[u.x >> 16]; v.z = row[u.y & 0xFFFFu]; v.w = row[u.y >> 16];
+                    st_cs_f4(reinterpret_cast<float4*>(p.sp_cube + (size_t)(g + t) * RK) + q, v);
                 }
                 if (p.cab_fast) {
-                    // first-max over this group's 4 slots, then over the G lanes of the window
-                    uint32_t key = order_key(v.x), off = 0;
-                    { uint32_t k2 = order_key(v.y); if (k2 > key) { key = k2; off = 1; } }
-                    { uint32_t k2 = order_key(v.z); if (k2 > key) { key = k2; off = 2; } }
-                    { uint32_t k2 = order_key(v.w); if (k2 > key) { key = k2; off = 3; } }
-                    float best = off == 0 ? v.x : off == 1 ? v.y : off == 2 ? v.z : v.w;
-                    off += (uint32_t)(q & (G - 1)) << 2;             // offset inside the window
-                    for (int d = 1; d < G; d <<= 1) {
-                        const uint32_t k2 = __shfl_xor_sync(0xFFFFFFFFu, key, d);
-                        const uint32_t o2 = __shfl_xor_sync(0xFFFFFFFFu, off, d);
-                        const float b2 = __shfl_xor_sync(0xFFFFFFFFu, best, d);
-                        if (k2 > key || (k2 == key && o2 < off)) { key = k2; off = o2; best = b2; }
+                    // torch.max over the window: first maximum, a NaN wins (first NaN); -0 == +0.
+                    // local winner of this item's 4 slots with plain float compares ...
+                    float best = v.x; uint32_t off = 0;
+                    if (!(v.y <= best) && best == best) { best = v.y; off = 1; }
+                    if (!(v.z <= best) && best == best) { best = v.z; off = 2; }
+                    if (!(v.w <= best) && best == best) { best = v.w; off = 3; }
+                    uint32_t woff = off + ((uint32_t)(q & (G - 1)) << 2);         // offset inside the window
+                    if (G > 1) {
+                        // ... then one packed word per lane: greater key wins, equal keys -> lower offset
+                        uint64_t pk = ((uint64_t)order_key(best) << 32) | (uint32_t)(0xFFFFFFFFu - woff);
+                        for (int d = 1; d < G; d <<= 1) {
+                            const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, pk, d);
+                            pk = o > pk ? o : pk;
+                        }
+                        woff = 0xFFFFFFFFu - (uint32_t)pk;
                     }
                     if (live && (q & (G - 1)) == 0) {
-                        const size_t o = (size_t)g * wins_per_row + q / G;       // (r, w) flattened
-                        p.cabins[o] = best;
-                        p.cab_arg[o] = (uint16_t)off;
+                        const int win = q >> p.g_shift;                            // (r, w) flattened
+                        const size_t o = (size_t)(g + t) * wins_per_row + win;
+                        // the value itself (sign of zero, NaN payload) comes from the winning slot
+                        p.cabins[o] = (G == 1) ? best : row[idx_s[win * wl + (int)woff]];
+                        p.cab_arg[o] = (uint16_t)woff;
                     }
                 }
             }
         } else {
-            for (int sidx = tt; sidx < RK; sidx += team_threads) orow[sidx] = row[__ldg(ib + sidx)];
+            const int items = rows * RK;
+            for (int e = tid; e < items; e += G_THREADS) {
+                const int t = e / RK, s = e - t * RK;
+                p.sp_cube[(size_t)(g + t) * RK + s] = tile[(size_t)t * N + idx_s[s]];
+            }
         }
-        // release the stage and refill it with the row `stages` ahead
-        team_sync(team, team_threads);
-        if (p.bulk_ok && tt == 0 && it + p.stages < my_count) {
-            mbar_expect_tx(&my_bars[s], (uint32_t)N * 4u);
-            bulk_g2s(row, p.x + (size_t)(g + p.stages) * N, (uint32_t)N * 4u, &my_bars[s]);
+        g += rows;
+        // release the buffer and refill it with the tile two ahead
+        __syncthreads();
+        if (g_pref < g_hi) {
+            const int r = tile_rows(g_pref, g_hi, T, C);
+            if (tid == 0) issue(g_pref, r, buf);
+            g_pref += r;
         }
     }
 }
@@ -179,9 +213,215 @@ __global__ void sp_cabins_bwd_kernel(const float* __restrict__ g_cabins, const u
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward
+// backward (default): rank-bucketed scatter into a shared-memory accumulator
+//
+// grad_x[b,c,n] = sum over the slots (r,j) that selected point n of g[b,c,r,j], ascending r.
+// Per sample the CTA orders the R*k slots by RANK = number of lower regions that selected the same
+// point.  Slots of one rank hit pairwise different points, so a rank bucket is scattered without
+// conflicts and without atomics; buckets are processed in ascending rank with a barrier in between,
+// which fixes the summation order (ascending region) -> deterministic.  The slot list is shared by
+// all C rows of the sample; T rows are accumulated together (T independent read-modify-writes per
+// list entry), then leave as ONE TMA bulk store while the next tile is accumulated in the other buffer.
 // ---------------------------------------------------------------------------------------------
 struct GatherBwdParams {
+    const float* g_cube; const float* g_cabins; const int32_t* idx; const uint16_t* cab_arg;
+    float* grad_x;
+    long long rows;   // B*C
+    int C, N, R, k, cab;
+    int T;            // rows per tile (1, 2, 4 or 8)
+    int bulk_in;      // (R*k)%4==0 and g_cube 16B aligned -> gradient tiles arrive with cp.async.bulk
+    int bulk_out;     // N%4==0 and grad_x 16B aligned -> rows leave with cp.async.bulk
+};
+
+template <int T>
+__device__ __forceinline__ void scatter_bucket(const uint32_t* ent, int lo, int hi, const float* gs, float* ac,
+                                               int RK, int N, int tid) {
+    for (int e = lo + tid; e < hi; e += G_THREADS) {
+        const uint32_t en = ent[e];
+        const int n = (int)(en & 0xFFFFu), s = (int)(en >> 16);
+        float gv[T], av[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) { gv[t] = gs[t * RK + s]; av[t] = ac[t * N + n]; }
+#pragma unroll
+        for (int t = 0; t < T; ++t) ac[t * N + n] = av[t] + gv[t];
+    }
+}
+
+__global__ void __launch_bounds__(G_THREADS)
+sp_gather_bwd_kernel(const GatherBwdParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int roff[66];            // bucket offsets (ranks 0..63) + fill counters during the build
+    __shared__ int rcount[64];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int N = p.N, R = p.R, k = p.k, T = p.T, C = p.C;
+    const int RK = R * k;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                        // 2
+    uint32_t* ent = reinterpret_cast<uint32_t*>(smem_raw + 128);                   // RK   (slot << 16) | point, by rank
+    float* gbuf = reinterpret_cast<float*>(smem_raw + 128 + (((size_t)RK * 4 + 127) & ~(size_t)127));   // 2 * T*RK
+    float* acc = gbuf + 2 * (size_t)T * RK;                                        // 2 * T*N
+    // build scratch, aliased onto the accumulators (no store is in flight while a sample is (re)built)
+    uint16_t* idx_s = reinterpret_cast<uint16_t*>(acc);                            // RK  point of every slot
+    uint16_t* rank = idx_s + RK;                                                   // RK  rank of every slot
+    uint16_t* cnt = rank + RK;                                                     // N   per-point counter
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    __syncthreads();
+
+    long long g_lo, g_hi;
+    cta_range(p.rows, g_lo, g_hi);
+    const int wl = (p.g_cabins != nullptr) ? k / p.cab : 1;
+    const int wins = R * p.cab;
+    auto issue = [&](long long g, int rows, int buf) {             // tid 0 only
+        if (p.bulk_in) {
+            const uint32_t bytes = (uint32_t)rows * (uint32_t)RK * 4u;
+            mbar_expect_tx(&bars[buf], bytes);
+            bulk_g2s(gbuf + (size_t)buf * T * RK, p.g_cube + (size_t)g * RK, bytes, &bars[buf]);
+        }
+    };
+    long long g = g_lo, g_pref = g_lo;
+    if (tid == 0) {
+        for (int i = 0; i < 2 && g_pref < g_hi; ++i) { const int r = tile_rows(g_pref, g_hi, T, C); issue(g_pref, r, i); g_pref += r; }
+    } else {
+        for (int i = 0; i < 2 && g_pref < g_hi; ++i) g_pref += tile_rows(g_pref, g_hi, T, C);
+    }
+    int cur_b = -1, n_rank = 0;
+
+    for (int ti = 0; g < g_hi; ++ti) {
+        const int buf = ti & 1;
+        const int rows = tile_rows(g, g_hi, T, C);
+        const int b = (int)((unsigned)g / (unsigned)C);
+        // window-max gradient of this tile: fetch early, use after the gradient tile has landed
+        float cab_g = 0.f; int cab_dst = -1;
+        if (p.g_cabins != nullptr && tid < rows * wins) {          // rows*wins <= 8*R*cab; larger cases loop below
+            const int t = tid / wins, rw = tid - t * wins;
+            const int r = rw / p.cab, w = rw - r * p.cab;
+            const size_t o = (size_t)(g + t) * wins + rw;
+            cab_dst = t * RK + r * k + w * wl + (int)__ldg(p.cab_arg + o);
+            cab_g = __ldg(p.g_cabins + o);
+        }
+        if (b != cur_b) {
+            // ---- slot list of sample b ordered by rank: built once per sample segment of this CTA --------
+            cur_b = b;
+            if (p.bulk_out && tid == 0) bulk_wait_read<0>();           // scratch aliases the accumulators
+            __syncthreads();
+            for (int n = tid; n < N; n += G_THREADS) cnt[n] = 0;
+            if (tid < 64) rcount[tid] = 0;
+            stage_idx_u16(p.idx + (size_t)b * RK, idx_s, RK, tid);
+            __syncthreads();
+            int my_max = 0;
+            for (int r = 0; r < R; ++r) {                              // points are unique inside a region
+                for (int j = tid; j < k; j += G_THREADS) {
+                    const int n = idx_s[r * k + j];
+                    const int c = cnt[n];
+                    rank[r * k + j] = (uint16_t)c;
+                    cnt[n] = (uint16_t)(c + 1);
+                    my_max = max(my_max, c);
+                }
+                __syncthreads();
+            }
+            my_max = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)my_max);
+            if (lane == 0) atomicMax(&rcount[63], my_max);             // rcount[63] is free: R <= 64 -> ranks <= 63 ...
+            __syncthreads();
+            n_rank = min(rcount[63] + 1, R);                           // ... and rank 63 needs R == 64: handled below
+            __syncthreads();
+            if (tid == 0) rcount[63] = 0;
+            __syncthreads();
+            // bucket sizes (warp-aggregated), offsets, placement
+            const int RK_up = (RK + 31) & ~31;
+            for (int e = tid; e < RK_up; e += G_THREADS) {
+                const int rk = e < RK ? (int)rank[e] : -1;
+                for (int q = 0; q < n_rank; ++q) {
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, rk == q);
+                    if (m && lane == 0) atomicAdd(&rcount[q], __popc(m));
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int run = 0;
+                for (int q = 0; q < n_rank; ++q) { roff[q] = run; run += rcount[q]; rcount[q] = roff[q]; }
+                roff[n_rank] = run;
+            }
+            __syncthreads();
+            for (int e = tid; e < RK_up; e += G_THREADS) {
+                const int rk = e < RK ? (int)rank[e] : -1;
+                for (int q = 0; q < n_rank; ++q) {
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, rk == q);
+                    if (m) {
+                        int base = 0;
+                        if (lane == (__ffs(m) - 1)) base = atomicAdd(&rcount[q], __popc(m));
+                        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+                        if (rk == q) ent[base + __popc(m & ((1u << lane) - 1))] = ((uint32_t)e << 16) | (uint32_t)idx_s[e];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        float* gs = gbuf + (size_t)buf * T * RK;
+        float* ac = acc + (size_t)buf * T * N;
+        // acc[buf] was handed to the TMA store two tiles ago: wait until that store has READ it, then zero
+        if (p.bulk_out && tid == 0) bulk_wait_read<1>();
+        __syncthreads();
+        {
+            float4* a4 = reinterpret_cast<float4*>(ac);
+            const int n4 = (rows * N) >> 2;
+            for (int i = tid; i < n4; i += G_THREADS) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = (n4 << 2) + tid; i < rows * N; i += G_THREADS) ac[i] = 0.f;
+        }
+        if (p.bulk_in) {
+            mbar_wait(&bars[buf], (uint32_t)((ti >> 1) & 1));
+        } else {
+            const float* src = p.g_cube + (size_t)g * RK;
+            for (int i = tid; i < rows * RK; i += G_THREADS) gs[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        // fold the window-max gradient into the slot that won each window (unique slots)
+        if (p.g_cabins != nullptr) {
+            if (cab_dst >= 0) gs[cab_dst] += cab_g;
+            for (int e = tid + G_THREADS; e < rows * wins; e += G_THREADS) {
+                const int t = e / wins, rw = e - t * wins;
+                const int r = rw / p.cab, w = rw - r * p.cab;
+                const size_t o = (size_t)(g + t) * wins + rw;
+                gs[t * RK + r * k + w * wl + (int)__ldg(p.cab_arg + o)] += __ldg(p.g_cabins + o);
+            }
+        }
+        __syncthreads();
+        for (int q = 0; q < n_rank; ++q) {
+            const int lo = roff[q], hi = roff[q + 1];
+            if (lo == hi) break;                                       // ranks are dense: nothing beyond
+            switch (T) {
+                case 1: scatter_bucket<1>(ent, lo, hi, gs, ac, RK, N, tid); break;
+                case 2: scatter_bucket<2>(ent, lo, hi, gs, ac, RK, N, tid); break;
+                case 4: scatter_bucket<4>(ent, lo, hi, gs, ac, RK, N, tid); break;
+                default: scatter_bucket<8>(ent, lo, hi, gs, ac, RK, N, tid); break;
+            }
+            __syncthreads();
+        }
+        float* dst = p.grad_x + (size_t)g * N;
+        if (p.bulk_out) {
+            fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the TMA engine
+            __syncthreads();
+            if (tid == 0) {
+                bulk_s2g(dst, ac, (uint32_t)(rows * N) * 4u);
+                bulk_commit();
+            }
+        } else {
+            for (int i = tid; i < rows * N; i += G_THREADS) dst[i] = ac[i];
+            __syncthreads();
+        }
+        g += rows;
+        if (g_pref < g_hi) {                                  // gs[buf] is free: every thread passed a barrier after its reads
+            const int r = tile_rows(g_pref, g_hi, T, C);
+            if (tid == 0) issue(g_pref, r, buf);
+            g_pref += r;
+        }
+    }
+    if (p.bulk_out && tid == 0) bulk_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, "push" formulation (fallback when the inverse index does not fit shared memory or
+// R*k > 65535): region-ordered scatter into a shared-memory accumulator, TMA bulk store of the rows
+// ---------------------------------------------------------------------------------------------
+struct GatherBwdPushParams {
     const float* g_cube; const float* g_cabins; const int32_t* idx; const uint16_t* cab_arg;
     float* grad_x;
     long long rows;   // B*C
@@ -191,6 +431,7 @@ struct GatherBwdParams {
     int bulk_in;      // (R*k)%4==0 and g_cube 16B aligned -> g rows arrive with cp.async.bulk
     int nbuf;         // 2 = double-buffered acc/g (default), 1 = single (rows too large for two)
     int g_direct;     // 1 = upstream gradient read straight from global (R*k too large to stage)
+    int k_shift;      // log2(k) when k is a power of two, else -1
 };
 
 // Each CTA owns a contiguous range of global rows and walks it in groups of <= T rows that lie in
@@ -198,7 +439,7 @@ struct GatherBwdParams {
 // into acc[i&1], the upstream gradient of group i+1 is in flight (bulk load) and the rows of
 // group i-1 are still leaving (bulk store).
 __global__ void __launch_bounds__(256)
-sp_gather_bwd_kernel(const GatherBwdParams p) {
+sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int N = p.N, R = p.R, k = p.k, T = p.T, C = p.C;
@@ -284,7 +525,8 @@ sp_gather_bwd_kernel(const GatherBwdParams p) {
         const int per_region = rows * k;
         for (int r = 0; r < R; ++r) {
             for (int e = tid; e < per_region; e += nthr) {
-                const int t = e / k, j = e - t * k;
+                int t, j;
+                if (p.k_shift >= 0) { t = e >> p.k_shift; j = e & (k - 1); } else { t = e / k; j = e - t * k; }
                 float gv;
                 if (!p.g_direct) {
                     gv = gs[t * RK + r * k + j];
@@ -323,10 +565,17 @@ sp_gather_bwd_kernel(const GatherBwdParams p) {
 
 }  // namespace spk
 
-static int occupancy_slots(const void* kernel, int threads, size_t smem) {
+static int occupancy_slots(const void* kernel, int threads, size_t smem, int cap_per_sm) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;
     return per_sm * spk::sm_count();
+}
+static int ilog2_exact(int v) {            // log2(v) if v is a power of two, else -1
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int s = 0;
+    while ((1 << s) < v) ++s;
+    return s;
 }
 
 extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int C, int N, int R,
@@ -343,38 +592,38 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
         if (cab < 1 || k < cab) return fail(SPK_E_BADARG, "sp_gather_fwd_f32: need 1 <= cab <= k (cab=%d k=%d)", cab, k);
         if (k / cab > 65535) return fail(SPK_E_UNSUPPORTED, "sp_gather_fwd_f32: window length k/cab=%d > 65535", k / cab);
     }
+    if (N > 65536) return fail(SPK_E_UNSUPPORTED, "sp_gather_fwd_f32: N=%d > 65536", N);
+    if ((long long)B * C >= (1LL << 31)) return fail(SPK_E_UNSUPPORTED, "sp_gather_fwd_f32: B*C >= 2^31");
     const long long RK = (long long)R * k;
-    if (RK > (1LL << 30)) return fail(SPK_E_UNSUPPORTED, "sp_gather_fwd_f32: R*k too large");
+    const size_t budget = (size_t)max_optin_smem();
+    const size_t fixed = 128 + (((size_t)RK * 2 + 127) & ~(size_t)127);
+    const size_t row_bytes = (size_t)N * 4;
+    if (fixed + 2 * row_bytes > budget)
+        return fail(SPK_E_UNSUPPORTED, "sp_gather_fwd_f32: N=%d, R*k=%lld do not fit shared memory", N, RK);
 
     GatherFwdParams p;
     p.x = x; p.idx = idx; p.sp_cube = sp_cube; p.cabins = cabins; p.cab_arg = cab_arg;
     p.rows = (long long)B * C;
     p.C = C; p.N = N; p.R = R; p.k = k; p.cab = want_cab ? cab : 0;
     p.bulk_ok = ((N & 3) == 0) && (((uintptr_t)x & 15) == 0);
-    p.vec4 = ((k & 3) == 0) && (((uintptr_t)sp_cube & 15) == 0) && (((uintptr_t)idx & 15) == 0);
+    p.vec4 = ((k & 3) == 0) && (((uintptr_t)sp_cube & 15) == 0);
     const int wl = want_cab ? k / cab : 0;
-    p.cab_fast = want_cab && p.vec4 && (k % cab == 0) && (wl % 4 == 0) && ((wl >> 2) <= 32) &&
-                 (((wl >> 2) & ((wl >> 2) - 1)) == 0);
-    int threads;
-    const size_t budget = (size_t)max_optin_smem();
-    const size_t row_bytes = (size_t)N * 4;
-    p.stages = 2;
-    if (4 * 2 * row_bytes + 256 <= 72 * 1024) {
-        p.team_threads = 32;       // 4 warps, each streaming its own rows: 3 CTAs per SM at N=2048
-        threads = 128;
-    } else if (2 * row_bytes + 256 <= budget) {
-        p.team_threads = threads = 256;
-    } else {
-        return fail(SPK_E_UNSUPPORTED, "sp_gather_fwd_f32: a row of N=%d floats does not fit shared memory twice", N);
-    }
-    const int n_teams = threads / p.team_threads;
-    const size_t smem = (((size_t)n_teams * p.stages * 8 + 127) & ~(size_t)127) + (size_t)n_teams * p.stages * row_bytes;
+    const int G = wl >> 2;
+    p.cab_fast = want_cab && p.vec4 && (k % cab == 0) && (wl % 4 == 0) && G <= 32 && ilog2_exact(G) >= 0 &&
+                 (G == 1 || ((RK >> 2) % 32) == 0);
+    p.g_shift = p.cab_fast ? ilog2_exact(G) : 0;
+    p.q_shift = ilog2_exact((int)(RK >> 2));
+    // T rows per tile: two tiles of ~32 KB each -> 3 CTAs (24 warps) per SM
+    int T = (int)std::max<size_t>(1, std::min<size_t>(16, (32 * 1024) / row_bytes));
+    while (T > 1 && fixed + 2 * (size_t)T * row_bytes > budget) --T;
+    T = std::min(T, C);
+    p.T = T;
+    const size_t smem = fixed + 2 * (size_t)T * row_bytes;
     if (smem > 48 * 1024)
         SPK_CUDA(cudaFuncSetAttribute(sp_gather_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // persistent: one wave of CTAs, every team a balanced contiguous range of rows
-    long long grid = occupancy_slots((const void*)sp_gather_fwd_kernel, threads, smem);
-    grid = std::min<long long>(grid, (p.rows + n_teams - 1) / n_teams);
-    sp_gather_fwd_kernel<<<(int)grid, threads, smem, (cudaStream_t)stream>>>(p);
+    long long grid = occupancy_slots((const void*)sp_gather_fwd_kernel, G_THREADS, smem, 0);
+    grid = std::min<long long>(grid, (p.rows + T - 1) / T);
+    sp_gather_fwd_kernel<<<(int)grid, G_THREADS, smem, (cudaStream_t)stream>>>(p);
     SPK_LAUNCH_CHECK("sp_gather_fwd_kernel");
     if (want_cab && !p.cab_fast) {
         const long long n_rows = (long long)B * C * R;
@@ -383,6 +632,39 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
         sp_cabins_generic_kernel<<<gsz, 256, 0, (cudaStream_t)stream>>>(sp_cube, k, cab, n_rows, cabins, cab_arg);
         SPK_LAUNCH_CHECK("sp_cabins_generic_kernel");
     }
+    return SPK_OK;
+}
+
+static int gather_bwd_push(const float* g_cube, const float* g_cabins, const int32_t* idx,
+                           const uint16_t* cab_arg, int B, int C, int N, int R, int k, int cab,
+                           float* grad_x, cudaStream_t stream) {
+    using namespace spk;
+    const long long RK = (long long)R * k;
+    GatherBwdPushParams p;
+    p.g_cube = g_cube; p.g_cabins = g_cabins; p.idx = idx; p.cab_arg = cab_arg; p.grad_x = grad_x;
+    p.rows = (long long)B * C;
+    p.C = C; p.N = N; p.R = R; p.k = k; p.cab = g_cabins ? cab : 1;
+    p.bulk_out = ((N & 3) == 0) && (((uintptr_t)grad_x & 15) == 0);
+    p.bulk_in = ((RK & 3) == 0) && (((uintptr_t)g_cube & 15) == 0);
+    const size_t budget = (size_t)max_optin_smem();
+    const size_t fixed = 128 + (((size_t)RK * 2 + 127) & ~(size_t)127);
+    size_t per_T = 2 * ((size_t)N + (size_t)RK) * 4;                // double-buffered acc + g per row
+    p.k_shift = ilog2_exact(k);
+    p.nbuf = 2; p.g_direct = 0;
+    if (fixed + per_T > budget) { per_T /= 2; p.nbuf = 1; }
+    if (fixed + per_T > budget) { per_T = (size_t)N * 4; p.g_direct = 1; }
+    if (fixed + per_T > budget)
+        return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: N=%d, R*k=%lld do not fit shared memory", N, RK);
+    int T = (int)std::max<size_t>(1, std::min<size_t>(8, (72 * 1024 - std::min<size_t>(fixed, 72 * 1024)) / per_T));
+    T = std::min(T, C);
+    p.T = T;
+    const size_t smem = fixed + (size_t)T * per_T;
+    if (smem > 48 * 1024)
+        SPK_CUDA(cudaFuncSetAttribute(sp_gather_bwd_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = occupancy_slots((const void*)sp_gather_bwd_push_kernel, 256, smem, 0);
+    grid = std::min<long long>(grid, (p.rows + T - 1) / T);
+    sp_gather_bwd_push_kernel<<<(int)grid, 256, smem, stream>>>(p);
+    SPK_LAUNCH_CHECK("sp_gather_bwd_push_kernel");
     return SPK_OK;
 }
 
@@ -399,31 +681,31 @@ extern "C" int sp_gather_bwd_f32(const float* g_cube, const float* g_cabins, con
         if (cab < 1 || k < cab) return fail(SPK_E_BADARG, "sp_gather_bwd_f32: need 1 <= cab <= k");
     }
     if (N > 65536) return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: N=%d > 65536", N);
+    if ((long long)B * C >= (1LL << 31)) return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: B*C >= 2^31");
     const long long RK = (long long)R * k;
+    // rank-bucketed kernel: slot list (u32[RK]) + two gradient tiles + two accumulator tiles in shared memory
+    const size_t budget = (size_t)max_optin_smem();
+    const size_t fixed = 128 + (((size_t)RK * 4 + 127) & ~(size_t)127);
+    const size_t per_T = 2 * ((size_t)RK + (size_t)N) * 4;
+    const size_t scratch = (size_t)RK * 4 + (size_t)N * 2;            // build scratch aliased onto the accumulators
+    if (RK > 65535 || R > 63 || fixed + per_T > budget || 2 * (size_t)N * 4 < scratch)
+        return gather_bwd_push(g_cube, g_cabins, idx, cab_arg, B, C, N, R, k, cab, grad_x, (cudaStream_t)stream);
     GatherBwdParams p;
     p.g_cube = g_cube; p.g_cabins = g_cabins; p.idx = idx; p.cab_arg = cab_arg; p.grad_x = grad_x;
     p.rows = (long long)B * C;
     p.C = C; p.N = N; p.R = R; p.k = k; p.cab = g_cabins ? cab : 1;
-    p.bulk_out = ((N & 3) == 0) && (((uintptr_t)grad_x & 15) == 0);
     p.bulk_in = ((RK & 3) == 0) && (((uintptr_t)g_cube & 15) == 0);
-    const size_t budget = (size_t)max_optin_smem();
-    const size_t fixed = 128 + (((size_t)RK * 2 + 127) & ~(size_t)127);
-    size_t per_T = 2 * ((size_t)N + (size_t)RK) * 4;                // double-buffered acc + g per row
-    p.nbuf = 2; p.g_direct = 0;
-    if (fixed + per_T > budget) { per_T /= 2; p.nbuf = 1; }
-    if (fixed + per_T > budget) { per_T = (size_t)N * 4; p.g_direct = 1; }
-    if (fixed + per_T > budget)
-        return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: N=%d, R*k=%lld do not fit shared memory", N, RK);
-    // T rows per group: aim at ~72 KB per CTA (3 CTAs per SM)
-    int T = (int)std::max<size_t>(1, std::min<size_t>(8, (72 * 1024 - std::min<size_t>(fixed, 72 * 1024)) / per_T));
-    T = std::min(T, C);
+    p.bulk_out = ((N & 3) == 0) && (((uintptr_t)grad_x & 15) == 0);
+    int T = 8;                                                       // ~72 KB per CTA -> 3 CTAs (24 warps) per SM
+    while (T > 1 && fixed + (size_t)T * per_T > 74 * 1024) T >>= 1;
+    while (T > 1 && T > C) T >>= 1;
     p.T = T;
     const size_t smem = fixed + (size_t)T * per_T;
     if (smem > 48 * 1024)
         SPK_CUDA(cudaFuncSetAttribute(sp_gather_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long grid = occupancy_slots((const void*)sp_gather_bwd_kernel, 256, smem);
+    long long grid = occupancy_slots((const void*)sp_gather_bwd_kernel, G_THREADS, smem, 0);
     grid = std::min<long long>(grid, (p.rows + T - 1) / T);
-    sp_gather_bwd_kernel<<<(int)grid, 256, smem, (cudaStream_t)stream>>>(p);
+    sp_gather_bwd_kernel<<<(int)grid, G_THREADS, smem, (cudaStream_t)stream>>>(p);
     SPK_LAUNCH_CHECK("sp_gather_bwd_kernel");
     return SPK_OK;
 }

@@ -66,33 +66,54 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);                 // K2 survivors
     uint32_t* sk = reinterpret_cast<uint32_t*>(sel + K2);                  // E*256 keys, [e][t]
-    __shared__ uint32_t wsum[2][TOPK_THREADS / 32][2];
+    __shared__ int hist[3][TOPK_THREADS / 32][16];
     __shared__ int warp_tot[TOPK_THREADS / 32];
     const int tid = threadIdx.x;
     const int row = blockIdx.x;
     const int b = row / R, r = row - b * R;
     const float* krow = keys + (size_t)row * N;
+#ifdef SPK_TIMING
+    long long tq[8]; tq[0] = clock64();
+#define TQ(i) tq[i] = clock64()
+#else
+#define TQ(i)
+#endif
 
     // ---- 1. load: thread t owns the E consecutive points n = t*E .. t*E+E-1 ------------------------
+    // (all loads are issued before the first use: order_key is branch-free, nothing serialises them)
     const int n0 = tid * E;
     if ((E & 3) == 0 && (N & 3) == 0) {
-        for (int e = 0; e < E; e += 4) {
-            const int n = n0 + e;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const bool in = n < N;                                          // N%4==0: all four or none
-            if (in) v = __ldg(reinterpret_cast<const float4*>(krow + n));
-            sk[(e + 0) * TOPK_THREADS + tid] = in ? order_key(v.x) : 0u;   // pad 0 < every real key
-            sk[(e + 1) * TOPK_THREADS + tid] = in ? order_key(v.y) : 0u;
-            sk[(e + 2) * TOPK_THREADS + tid] = in ? order_key(v.z) : 0u;
-            sk[(e + 3) * TOPK_THREADS + tid] = in ? order_key(v.w) : 0u;
+        for (int e0 = 0; e0 < E; e0 += 16) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int n = n0 + e0 + 4 * u;
+                v[u] = (e0 + 4 * u < E && n < N) ? __ldg(reinterpret_cast<const float4*>(krow + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + 4 * u;
+                if (e < E) {
+                    const bool in = n0 + e < N;                             // N%4==0: all four or none
+                    sk[(e + 0) * TOPK_THREADS + tid] = in ? order_key(v[u].x) : 0u;   // pad 0 < every real key
+                    sk[(e + 1) * TOPK_THREADS + tid] = in ? order_key(v[u].y) : 0u;
+                    sk[(e + 2) * TOPK_THREADS + tid] = in ? order_key(v[u].z) : 0u;
+                    sk[(e + 3) * TOPK_THREADS + tid] = in ? order_key(v[u].w) : 0u;
+                }
+            }
         }
     } else {
-        for (int e = 0; e < E; ++e) {
-            const int n = n0 + e;
-            sk[e * TOPK_THREADS + tid] = (n < N) ? order_key(__ldg(krow + n)) : 0u;
+        for (int e0 = 0; e0 < E; e0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(krow + min(n0 + e0 + u, N - 1));
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (e0 + u < E) sk[(e0 + u) * TOPK_THREADS + tid] = (n0 + e0 + u < N) ? order_key(v[u]) : 0u;
         }
     }
     for (int i = tid; i < K2; i += TOPK_THREADS) sel[i] = 0ull;
+    for (int i = tid; i < 3 * 8 * 16; i += TOPK_THREADS) (&hist[0][0][0])[i] = 0;
 
     // ---- argmax over the R rows for this CTA's slice of n (softpool.py:95) --------------------------
     if (id_activa != nullptr) {
@@ -102,40 +123,58 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         for (int n = s0 + tid; n < s1; n += TOPK_THREADS) {
             uint32_t bestk = order_key(__ldg(kb + n));
             int besti = 0;
+#pragma unroll 8
             for (int rr = 1; rr < R; ++rr) {
                 const uint32_t kk = order_key(__ldg(kb + (size_t)rr * N + n));
-                if (kk > bestk) { bestk = kk; besti = rr; }   // strict: first maximum / first NaN
+                const bool better = kk > bestk;                  // strict: first maximum / first NaN
+                bestk = better ? kk : bestk; besti = better ? rr : besti;
             }
             id_activa[(size_t)b * N + n] = (int64_t)besti;
         }
     }
     __syncthreads();
+    TQ(1);
 
-    // ---- 2. radix select of the k-th largest key, 2 bits per round ---------------------------------------
+    // ---- 2. radix select of the k-th largest key, 4 bits per round ---------------------------------------
+    // Warp-private 16-bin histograms of the keys that still match the decided prefix (shared-memory
+    // atomics), one barrier per round; every warp then reduces the 8 histograms itself.
     uint32_t V = 0;
+    int want = k;                                        // rank still to be located inside the prefix bucket
     const int lane = tid & 31, warp = tid >> 5;
-    for (int round = 0; round < 16; ++round) {
-        const int sh = 30 - 2 * round;
-        const uint32_t T1 = V | (1u << sh), T2 = V | (2u << sh), T3 = V | (3u << sh);
-        uint32_t c12 = 0, c3 = 0;
+    for (int round = 0; round < 8; ++round) {
+        const int sh = 28 - 4 * round;
+        int* H = &hist[round % 3][0][0];
+        const uint32_t pre = (round == 0) ? 0u : (V >> (sh + 4));
 #pragma unroll 4
         for (int e = 0; e < E; ++e) {
             const uint32_t key = sk[e * TOPK_THREADS + tid];
-            c12 += (key >= T1 ? 1u : 0u) + (key >= T2 ? 0x10000u : 0u);
-            c3 += (key >= T3 ? 1u : 0u);
+            const bool cand = (round == 0) || ((key >> (sh + 4)) == pre);
+            if (cand) atomicAdd(&H[warp * 16 + ((key >> sh) & 15u)], 1);
         }
-        c12 = __reduce_add_sync(0xFFFFFFFFu, c12);      // per-warp counts <= 32*64 fit 16 bits
-        c3 = __reduce_add_sync(0xFFFFFFFFu, c3);
-        const int buf = round & 1;
-        if (lane == 0) { wsum[buf][warp][0] = c12; wsum[buf][warp][1] = c3; }
         __syncthreads();
-        uint32_t t12 = 0, t3 = 0;
+        int c = 0;
+        if (lane < 16) {
 #pragma unroll
-        for (int w = 0; w < TOPK_THREADS / 32; ++w) { t12 += wsum[buf][w][0]; t3 += wsum[buf][w][1]; }
-        const uint32_t n1 = t12 & 0xFFFFu, n2 = t12 >> 16;        // totals <= 16384
-        if (t3 >= (uint32_t)k) V = T3; else if (n2 >= (uint32_t)k) V = T2; else if (n1 >= (uint32_t)k) V = T1;
+            for (int w = 0; w < TOPK_THREADS / 32; ++w) c += H[w * 16 + lane];
+        }
+        // suffix sums over digits: S(d) = # candidates with digit >= d   (lanes >= 16 hold 0)
+        int S = c;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            const int o = __shfl_down_sync(0xFFFFFFFFu, S, d);
+            if (lane + d < 16) S += o;
+        }
+        const unsigned ok = __ballot_sync(0xFFFFFFFFu, lane < 16 && S >= want);   // digits whose suffix reaches the rank
+        const int dsel = 31 - __clz((int)ok);                                      // the largest such digit (bit 0 is always set)
+        const int above = __shfl_sync(0xFFFFFFFFu, S - c, dsel);                   // candidates with a larger digit
+        want -= above;
+        V |= (uint32_t)dsel << sh;
+        // recycle the histogram used two rounds from now (everybody is past the barrier of the previous round)
+        int* Hz = &hist[(round + 2) % 3][0][0];
+        if (tid < 8 * 16) Hz[tid] = 0;
     }
 
+    TQ(2);
     // ---- 3. compaction in index order ---------------------------------------------------------------------
     int my_gt = 0, my_eq = 0;
 #pragma unroll 4
@@ -158,6 +197,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         if (take) { sel[pos++] = ((uint64_t)key << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)(n0 + e)); }
     }
 
+    TQ(3);
     // ---- 4. sort the survivors (descending; unique words => stable order) ---------------------------------
     int prev = 64;
     for (int size = 2; size <= K2; size <<= 1)
@@ -167,6 +207,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
             prev = stride;
         }
     __syncthreads();
+    TQ(4);
 
     // ---- emit ---------------------------------------------------------------------------------------------
     int32_t* orow = idx + (size_t)row * k;
@@ -178,6 +219,12 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
             sp_idx[(((size_t)b * Q + q) * R + r) * k + j] = (float)(0xFFFFFFFFu - (uint32_t)sel[j]);
         }
     }
+#ifdef SPK_TIMING
+    TQ(5);
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 200))
+        printf("topk cta %d: load+argmax %lld  select %lld  compact %lld  sort %lld  emit %lld  (cycles)\n", blockIdx.x,
+               tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], tq[5] - tq[4]);
+#endif
 }
 
 __global__ void sp_argmax_kernel(const float* __restrict__ keys, int R, int N,

@@ -43,10 +43,12 @@ static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p;
 // float32 -> uint32 whose unsigned order is the order torch.sort(descending=True) uses on CPU:
 // NaN greatest (all NaNs tie), -0 == +0.  Same transform as oracle/softpool_oracle.py:order_key.
 __device__ __forceinline__ uint32_t order_key(float f) {
-    uint32_t b = __float_as_uint(f);
-    if ((b & 0x7FFFFFFFu) > 0x7F800000u) return 0xFFFFFFFFu;   // NaN
-    if (b == 0x80000000u) b = 0u;                                // -0 -> +0
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    // branch-free (selects only): keeps loads around it free to be hoisted and batched
+    const uint32_t b = __float_as_uint(f);
+    uint32_t m = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    m = (b == 0x80000000u) ? 0x80000000u : m;                    // -0 -> the key of +0
+    m = ((b & 0x7FFFFFFFu) > 0x7F800000u) ? 0xFFFFFFFFu : m;     // NaN
+    return m;
 }
 
 // ---- mbarrier + bulk async copy (TMA, 1-D form: SASS UBLKCP) -----------------------------------
