@@ -1,6 +1,7 @@
 // capi.cu -- error plumbing and device-attribute caches of libsoftpool_b200.
 #include "spk_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace spk {
 
@@ -34,6 +35,12 @@ int sm_count() {
         g_sm[dev] = v;
     }
     return g_sm[dev];
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SPK_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
 }
 
 int max_optin_smem() {

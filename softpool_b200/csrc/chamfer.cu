@@ -25,6 +25,8 @@ chamfer_nn_exact_kernel(const float* __restrict__ xyz1, const float* __restrict_
                         float* __restrict__ dist1, float* __restrict__ dist2,
                         int32_t* __restrict__ idx1, int32_t* __restrict__ idx2) {
     __shared__ float4 tgt[CH_CHUNK];
+    pdl_trigger();
+    pdl_wait();
     const int dir = blockIdx.z, b = blockIdx.y;
     const float* Q = dir == 0 ? xyz1 : xyz2;
     const float* T = dir == 0 ? xyz2 : xyz1;
@@ -77,6 +79,8 @@ __global__ void chamfer_bwd_direct_kernel(const float* __restrict__ xyz1, const 
                                           const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2,
                                           int n, int m, float* __restrict__ grad1, float* __restrict__ grad2,
                                           long long total1, long long total2) {
+    pdl_trigger();
+    pdl_wait();
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total1 + total2;
          t += (long long)gridDim.x * blockDim.x) {
         const bool first = t < total1;
@@ -99,6 +103,8 @@ __global__ void chamfer_bwd_scatter_kernel(const float* __restrict__ xyz1, const
                                            const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2,
                                            int n, int m, float* __restrict__ grad1, float* __restrict__ grad2,
                                            long long total1, long long total2) {
+    pdl_trigger();
+    pdl_wait();
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total1 + total2;
          t += (long long)gridDim.x * blockDim.x) {
         const bool first = t < total1;
@@ -122,6 +128,8 @@ __global__ void __launch_bounds__(256)
 chamfer_loss_kernel(const float* __restrict__ dist1, const float* __restrict__ dist2, int n, int m,
                     float* __restrict__ loss) {
     __shared__ float red[2][8];
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x, tid = threadIdx.x;
     float s1 = 0.f, s2 = 0.f;
     for (int i = tid; i < n; i += 256) s1 += dist1[(size_t)b * n + i];
@@ -172,8 +180,7 @@ extern "C" int chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int 
     if (use_tensor_path(n, m)) return chamfer_tc_forward(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, ws, ws_bytes, st);
     const int per = CH_THREADS * CH_QPT;
     dim3 grid((max(n, m) + per - 1) / per, B, 2);
-    chamfer_nn_exact_kernel<<<grid, CH_THREADS, 0, st>>>(xyz1, xyz2, n, m, dist1, dist2, idx1, idx2);
-    SPK_LAUNCH_CHECK("chamfer_nn_exact_kernel");
+    SPK_CUDA(launch_k(chamfer_nn_exact_kernel, grid, dim3(CH_THREADS), 0, st, xyz1, xyz2, n, m, dist1, dist2, idx1, idx2));
     return SPK_OK;
 }
 
@@ -193,10 +200,8 @@ extern "C" int chamfer_bwd_f32(const float* xyz1, const float* xyz2, const float
         return fail(SPK_E_BADARG, "chamfer_bwd_f32: null pointer");
     const long long t1 = (long long)B * n, t2 = (long long)B * m;
     const int grid = (int)std::min<long long>((t1 + t2 + 255) / 256, (long long)sm_count() * 8);
-    chamfer_bwd_direct_kernel<<<grid, 256, 0, st>>>(xyz1, xyz2, g1, g2, idx1, idx2, n, m, grad_xyz1, grad_xyz2, t1, t2);
-    SPK_LAUNCH_CHECK("chamfer_bwd_direct_kernel");
-    chamfer_bwd_scatter_kernel<<<grid, 256, 0, st>>>(xyz1, xyz2, g1, g2, idx1, idx2, n, m, grad_xyz1, grad_xyz2, t1, t2);
-    SPK_LAUNCH_CHECK("chamfer_bwd_scatter_kernel");
+    SPK_CUDA(launch_k(chamfer_bwd_direct_kernel, dim3(grid), dim3(256), 0, st, xyz1, xyz2, g1, g2, idx1, idx2, n, m, grad_xyz1, grad_xyz2, t1, t2));
+    SPK_CUDA(launch_k(chamfer_bwd_scatter_kernel, dim3(grid), dim3(256), 0, st, xyz1, xyz2, g1, g2, idx1, idx2, n, m, grad_xyz1, grad_xyz2, t1, t2));
     return SPK_OK;
 }
 
@@ -206,7 +211,6 @@ extern "C" int chamfer_loss_f32(const float* dist1, const float* dist2, int B, i
     if (B < 0 || n < 1 || m < 1) return fail(SPK_E_BADARG, "chamfer_loss_f32: need B>=0, n,m>=1");
     if (B == 0) return SPK_OK;
     if (!dist1 || !dist2 || !loss) return fail(SPK_E_BADARG, "chamfer_loss_f32: null pointer");
-    chamfer_loss_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(dist1, dist2, n, m, loss);
-    SPK_LAUNCH_CHECK("chamfer_loss_kernel");
+    SPK_CUDA(launch_k(chamfer_loss_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, dist1, dist2, n, m, loss));
     return SPK_OK;
 }

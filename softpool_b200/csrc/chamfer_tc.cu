@@ -107,17 +107,32 @@ __global__ void __launch_bounds__(256)
 chamfer_prep_kernel(const PrepParams p) {
     __shared__ float red[6][8];
     __shared__ float s_meta[8];
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y, tid = threadIdx.x;
     const float* P = p.xyz1 + (size_t)b * p.n * 3;
     const float* Q = p.xyz2 + (size_t)b * p.m * 3;
-    // bounding box over both clouds (every CTA of the sample recomputes it: 12*(n+m) bytes from L2)
+    // bounding box over both clouds (every CTA of the sample recomputes it: 12*(n+m) bytes from L2).
+    // 128-bit loads, three per step = four whole points, so the axis of every lane is static.
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = tid; i < p.n; i += 256)
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { const float v = __ldg(P + 3 * i + a); lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
-    for (int i = tid; i < p.m; i += 256)
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { const float v = __ldg(Q + 3 * i + a); lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    auto upd = [&](int a, float v) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); };
+    for (int c = 0; c < 2; ++c) {
+        const float* X = c ? Q : P;
+        const int cnt = c ? p.m : p.n;
+        int done = 0;
+        if ((((uintptr_t)X) & 15) == 0) {
+            const int steps = cnt / 4;                               // 4 points = 12 floats = 3 float4
+            const float4* X4 = reinterpret_cast<const float4*>(X);
+            for (int st = tid; st < steps; st += 256) {
+                const float4 a = __ldg(X4 + 3 * st), b4 = __ldg(X4 + 3 * st + 1), c4 = __ldg(X4 + 3 * st + 2);
+                upd(0, a.x); upd(1, a.y); upd(2, a.z); upd(0, a.w);
+                upd(1, b4.x); upd(2, b4.y); upd(0, b4.z); upd(1, b4.w);
+                upd(2, c4.x); upd(0, c4.y); upd(1, c4.z); upd(2, c4.w);
+            }
+            done = steps * 4;
+        }
+        for (int i = done + tid; i < cnt; i += 256) { upd(0, __ldg(X + 3 * i)); upd(1, __ldg(X + 3 * i + 1)); upd(2, __ldg(X + 3 * i + 2)); }
+    }
 #pragma unroll
     for (int a = 0; a < 3; ++a)
         for (int d = 16; d > 0; d >>= 1) {
@@ -305,10 +320,12 @@ chamfer_tc_kernel(const TcParams p) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
+    pdl_wait();                  // operands / metadata come from chamfer_prep_kernel
 
     // running counters (identical in every role): B-ring slots, accumulator buffers, super-blocks, jobs
     uint32_t ring_it = 0, acc_it = 0, sb_it = 0, job_it = 0;
@@ -493,9 +510,8 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
     pp.A1 = ops; pp.B1 = pp.A1 + (size_t)B * n_pad * 32;
     pp.A2 = pp.B1 + (size_t)B * n_pad * 32; pp.B2 = pp.A2 + (size_t)B * m_pad * 32;
     pp.T1 = reinterpret_cast<float4*>(pp.B2 + (size_t)B * m_pad * 32); pp.T2 = pp.T1 + (size_t)B * n_pad;
-    const int slices = std::max(1, std::min(8, (n_pad + m_pad) / 1024));
-    chamfer_prep_kernel<<<dim3(slices, B), 256, 0, st>>>(pp);
-    SPK_LAUNCH_CHECK("chamfer_prep_kernel");
+    const int slices = std::max(1, std::min(16, (n_pad + m_pad) / 512));
+    SPK_CUDA(launch_k(chamfer_prep_kernel, dim3(slices, B), dim3(256), 0, st, pp));
 
     TcParams tp;
     tp.xyz1 = xyz1; tp.xyz2 = xyz2; tp.A1 = pp.A1; tp.B1 = pp.B1; tp.A2 = pp.A2; tp.B2 = pp.B2; tp.T1 = pp.T1; tp.T2 = pp.T2; tp.meta = pp.meta; tp.B = B;
@@ -507,8 +523,7 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
     SPK_CUDA(cudaFuncSetAttribute(chamfer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long jobs = (long long)(tp.tiles1 + tp.tiles2) * B;
     const int grid = (int)std::min<long long>(jobs, 2LL * sm_count());         // persistent: 2 CTAs per SM
-    chamfer_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tp);
-    SPK_LAUNCH_CHECK("chamfer_tc_kernel");
+    SPK_CUDA(launch_k(chamfer_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tp));
     return SPK_OK;
 }
 

@@ -9,12 +9,11 @@
 //     copy (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP), double-buffered, so the random
 //     index access hits shared memory, never HBM/L2, and every x byte is read exactly once; the
 //     sample's index list sits in shared memory as u16; outputs leave as 128-bit streaming stores;
-//   * backward: per sample the CTA orders the R*k slots by rank (number of lower regions that chose
-//     the same point); slots of one rank hit different points, so a rank bucket is scattered into
-//     a T x N shared-memory accumulator without conflicts or atomics, buckets in ascending rank
-//     (= ascending region: deterministic order); the T finished rows leave with one TMA bulk store
-//     (cp.async.bulk.global.shared::cta) while the next tile is accumulated in the other buffer.
-//     grad_x is fully overwritten (zeros included): no memset.
+//   * backward: the upstream gradient tile arrives by bulk copy; one region per phase is scattered
+//     into a T x N shared-memory accumulator (points are unique inside a region: no conflicts, no
+//     atomics; ascending regions = fixed summation order); the T finished rows leave with one TMA
+//     bulk store (cp.async.bulk.global.shared::cta) while the next tile is accumulated in the other
+//     buffer.  grad_x is fully overwritten (zeros included): no memset.
 #include "spk_common.cuh"
 
 namespace spk {
@@ -74,7 +73,9 @@ sp_gather_fwd_kernel(const GatherFwdParams p) {
     uint16_t* idx_s = reinterpret_cast<uint16_t*>(smem_raw + 128);                     // RK
     float* tiles = reinterpret_cast<float*>(smem_raw + 128 + ((RK * 2 + 127) & ~127)); // 2 * T*N
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();
 
     long long g_lo, g_hi;
     cta_range(p.rows, g_lo, g_hi);
@@ -178,6 +179,8 @@ sp_gather_fwd_kernel(const GatherFwdParams p) {
 __global__ void sp_cabins_generic_kernel(const float* __restrict__ sp_cube, int k, int cab,
                                          long long n_rows /* B*C*R */, float* __restrict__ cabins,
                                          uint16_t* __restrict__ cab_arg) {
+    pdl_trigger();
+    pdl_wait();
     const int wl = k / cab;
     const long long total = n_rows * cab;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -197,6 +200,8 @@ __global__ void sp_cabins_generic_kernel(const float* __restrict__ sp_cube, int 
 // Backward of the standalone window max: g_windows[row, w*wl + arg] = g_cabins[row, w], else 0.
 __global__ void sp_cabins_bwd_kernel(const float* __restrict__ g_cabins, const uint16_t* __restrict__ cab_arg,
                                      int k, int cab, long long total /* rows*k */, float* __restrict__ g_windows) {
+    pdl_trigger();
+    pdl_wait();
     const int wl = k / cab;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
@@ -213,213 +218,11 @@ __global__ void sp_cabins_bwd_kernel(const float* __restrict__ g_cabins, const u
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward (default): rank-bucketed scatter into a shared-memory accumulator
-//
-// grad_x[b,c,n] = sum over the slots (r,j) that selected point n of g[b,c,r,j], ascending r.
-// Per sample the CTA orders the R*k slots by RANK = number of lower regions that selected the same
-// point.  Slots of one rank hit pairwise different points, so a rank bucket is scattered without
-// conflicts and without atomics; buckets are processed in ascending rank with a barrier in between,
-// which fixes the summation order (ascending region) -> deterministic.  The slot list is shared by
-// all C rows of the sample; T rows are accumulated together (T independent read-modify-writes per
-// list entry), then leave as ONE TMA bulk store while the next tile is accumulated in the other buffer.
-// ---------------------------------------------------------------------------------------------
-struct GatherBwdParams {
-    const float* g_cube; const float* g_cabins; const int32_t* idx; const uint16_t* cab_arg;
-    float* grad_x;
-    long long rows;   // B*C
-    int C, N, R, k, cab;
-    int T;            // rows per tile (1, 2, 4 or 8)
-    int bulk_in;      // (R*k)%4==0 and g_cube 16B aligned -> gradient tiles arrive with cp.async.bulk
-    int bulk_out;     // N%4==0 and grad_x 16B aligned -> rows leave with cp.async.bulk
-};
-
-template <int T>
-__device__ __forceinline__ void scatter_bucket(const uint32_t* ent, int lo, int hi, const float* gs, float* ac,
-                                               int RK, int N, int tid) {
-    for (int e = lo + tid; e < hi; e += G_THREADS) {
-        const uint32_t en = ent[e];
-        const int n = (int)(en & 0xFFFFu), s = (int)(en >> 16);
-        float gv[T], av[T];
-#pragma unroll
-        for (int t = 0; t < T; ++t) { gv[t] = gs[t * RK + s]; av[t] = ac[t * N + n]; }
-#pragma unroll
-        for (int t = 0; t < T; ++t) ac[t * N + n] = av[t] + gv[t];
-    }
-}
-
-__global__ void __launch_bounds__(G_THREADS)
-sp_gather_bwd_kernel(const GatherBwdParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int roff[66];            // bucket offsets (ranks 0..63) + fill counters during the build
-    __shared__ int rcount[64];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int N = p.N, R = p.R, k = p.k, T = p.T, C = p.C;
-    const int RK = R * k;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                        // 2
-    uint32_t* ent = reinterpret_cast<uint32_t*>(smem_raw + 128);                   // RK   (slot << 16) | point, by rank
-    float* gbuf = reinterpret_cast<float*>(smem_raw + 128 + (((size_t)RK * 4 + 127) & ~(size_t)127));   // 2 * T*RK
-    float* acc = gbuf + 2 * (size_t)T * RK;                                        // 2 * T*N
-    // build scratch, aliased onto the accumulators (no store is in flight while a sample is (re)built)
-    uint16_t* idx_s = reinterpret_cast<uint16_t*>(acc);                            // RK  point of every slot
-    uint16_t* rank = idx_s + RK;                                                   // RK  rank of every slot
-    uint16_t* cnt = rank + RK;                                                     // N   per-point counter
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
-    __syncthreads();
-
-    long long g_lo, g_hi;
-    cta_range(p.rows, g_lo, g_hi);
-    const int wl = (p.g_cabins != nullptr) ? k / p.cab : 1;
-    const int wins = R * p.cab;
-    auto issue = [&](long long g, int rows, int buf) {             // tid 0 only
-        if (p.bulk_in) {
-            const uint32_t bytes = (uint32_t)rows * (uint32_t)RK * 4u;
-            mbar_expect_tx(&bars[buf], bytes);
-            bulk_g2s(gbuf + (size_t)buf * T * RK, p.g_cube + (size_t)g * RK, bytes, &bars[buf]);
-        }
-    };
-    long long g = g_lo, g_pref = g_lo;
-    if (tid == 0) {
-        for (int i = 0; i < 2 && g_pref < g_hi; ++i) { const int r = tile_rows(g_pref, g_hi, T, C); issue(g_pref, r, i); g_pref += r; }
-    } else {
-        for (int i = 0; i < 2 && g_pref < g_hi; ++i) g_pref += tile_rows(g_pref, g_hi, T, C);
-    }
-    int cur_b = -1, n_rank = 0;
-
-    for (int ti = 0; g < g_hi; ++ti) {
-        const int buf = ti & 1;
-        const int rows = tile_rows(g, g_hi, T, C);
-        const int b = (int)((unsigned)g / (unsigned)C);
-        // window-max gradient of this tile: fetch early, use after the gradient tile has landed
-        float cab_g = 0.f; int cab_dst = -1;
-        if (p.g_cabins != nullptr && tid < rows * wins) {          // rows*wins <= 8*R*cab; larger cases loop below
-            const int t = tid / wins, rw = tid - t * wins;
-            const int r = rw / p.cab, w = rw - r * p.cab;
-            const size_t o = (size_t)(g + t) * wins + rw;
-            cab_dst = t * RK + r * k + w * wl + (int)__ldg(p.cab_arg + o);
-            cab_g = __ldg(p.g_cabins + o);
-        }
-        if (b != cur_b) {
-            // ---- slot list of sample b ordered by rank: built once per sample segment of this CTA --------
-            cur_b = b;
-            if (p.bulk_out && tid == 0) bulk_wait_read<0>();           // scratch aliases the accumulators
-            __syncthreads();
-            for (int n = tid; n < N; n += G_THREADS) cnt[n] = 0;
-            if (tid < 64) rcount[tid] = 0;
-            stage_idx_u16(p.idx + (size_t)b * RK, idx_s, RK, tid);
-            __syncthreads();
-            int my_max = 0;
-            for (int r = 0; r < R; ++r) {                              // points are unique inside a region
-                for (int j = tid; j < k; j += G_THREADS) {
-                    const int n = idx_s[r * k + j];
-                    const int c = cnt[n];
-                    rank[r * k + j] = (uint16_t)c;
-                    cnt[n] = (uint16_t)(c + 1);
-                    my_max = max(my_max, c);
-                }
-                __syncthreads();
-            }
-            my_max = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)my_max);
-            if (lane == 0) atomicMax(&rcount[63], my_max);             // rcount[63] is free: R <= 64 -> ranks <= 63 ...
-            __syncthreads();
-            n_rank = min(rcount[63] + 1, R);                           // ... and rank 63 needs R == 64: handled below
-            __syncthreads();
-            if (tid == 0) rcount[63] = 0;
-            __syncthreads();
-            // bucket sizes (warp-aggregated), offsets, placement
-            const int RK_up = (RK + 31) & ~31;
-            for (int e = tid; e < RK_up; e += G_THREADS) {
-                const int rk = e < RK ? (int)rank[e] : -1;
-                for (int q = 0; q < n_rank; ++q) {
-                    const unsigned m = __ballot_sync(0xFFFFFFFFu, rk == q);
-                    if (m && lane == 0) atomicAdd(&rcount[q], __popc(m));
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int run = 0;
-                for (int q = 0; q < n_rank; ++q) { roff[q] = run; run += rcount[q]; rcount[q] = roff[q]; }
-                roff[n_rank] = run;
-            }
-            __syncthreads();
-            for (int e = tid; e < RK_up; e += G_THREADS) {
-                const int rk = e < RK ? (int)rank[e] : -1;
-                for (int q = 0; q < n_rank; ++q) {
-                    const unsigned m = __ballot_sync(0xFFFFFFFFu, rk == q);
-                    if (m) {
-                        int base = 0;
-                        if (lane == (__ffs(m) - 1)) base = atomicAdd(&rcount[q], __popc(m));
-                        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-                        if (rk == q) ent[base + __popc(m & ((1u << lane) - 1))] = ((uint32_t)e << 16) | (uint32_t)idx_s[e];
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        float* gs = gbuf + (size_t)buf * T * RK;
-        float* ac = acc + (size_t)buf * T * N;
-        // acc[buf] was handed to the TMA store two tiles ago: wait until that store has READ it, then zero
-        if (p.bulk_out && tid == 0) bulk_wait_read<1>();
-        __syncthreads();
-        {
-            float4* a4 = reinterpret_cast<float4*>(ac);
-            const int n4 = (rows * N) >> 2;
-            for (int i = tid; i < n4; i += G_THREADS) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = (n4 << 2) + tid; i < rows * N; i += G_THREADS) ac[i] = 0.f;
-        }
-        if (p.bulk_in) {
-            mbar_wait(&bars[buf], (uint32_t)((ti >> 1) & 1));
-        } else {
-            const float* src = p.g_cube + (size_t)g * RK;
-            for (int i = tid; i < rows * RK; i += G_THREADS) gs[i] = __ldg(src + i);
-            __syncthreads();
-        }
-        // fold the window-max gradient into the slot that won each window (unique slots)
-        if (p.g_cabins != nullptr) {
-            if (cab_dst >= 0) gs[cab_dst] += cab_g;
-            for (int e = tid + G_THREADS; e < rows * wins; e += G_THREADS) {
-                const int t = e / wins, rw = e - t * wins;
-                const int r = rw / p.cab, w = rw - r * p.cab;
-                const size_t o = (size_t)(g + t) * wins + rw;
-                gs[t * RK + r * k + w * wl + (int)__ldg(p.cab_arg + o)] += __ldg(p.g_cabins + o);
-            }
-        }
-        __syncthreads();
-        for (int q = 0; q < n_rank; ++q) {
-            const int lo = roff[q], hi = roff[q + 1];
-            if (lo == hi) break;                                       // ranks are dense: nothing beyond
-            switch (T) {
-                case 1: scatter_bucket<1>(ent, lo, hi, gs, ac, RK, N, tid); break;
-                case 2: scatter_bucket<2>(ent, lo, hi, gs, ac, RK, N, tid); break;
-                case 4: scatter_bucket<4>(ent, lo, hi, gs, ac, RK, N, tid); break;
-                default: scatter_bucket<8>(ent, lo, hi, gs, ac, RK, N, tid); break;
-            }
-            __syncthreads();
-        }
-        float* dst = p.grad_x + (size_t)g * N;
-        if (p.bulk_out) {
-            fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the TMA engine
-            __syncthreads();
-            if (tid == 0) {
-                bulk_s2g(dst, ac, (uint32_t)(rows * N) * 4u);
-                bulk_commit();
-            }
-        } else {
-            for (int i = tid; i < rows * N; i += G_THREADS) dst[i] = ac[i];
-            __syncthreads();
-        }
-        g += rows;
-        if (g_pref < g_hi) {                                  // gs[buf] is free: every thread passed a barrier after its reads
-            const int r = tile_rows(g_pref, g_hi, T, C);
-            if (tid == 0) issue(g_pref, r, buf);
-            g_pref += r;
-        }
-    }
-    if (p.bulk_out && tid == 0) bulk_wait<0>();
-}
-
-// ---------------------------------------------------------------------------------------------
-// backward, "push" formulation (fallback when the inverse index does not fit shared memory or
-// R*k > 65535): region-ordered scatter into a shared-memory accumulator, TMA bulk store of the rows
+// backward: region-ordered scatter into a shared-memory accumulator, TMA bulk store of the rows.
+// grad_x[b,c,n] = sum over the slots (r,j) that selected point n of g[b,c,r,j].  Points are unique
+// inside a region, so one region is scattered per phase without conflicts or atomics; regions in
+// ascending order fix the summation order -> deterministic.  (Tried and measured slower on B200,
+// see profiles/README.md: a CSR "pull" formulation and a rank-bucketed scatter.)
 // ---------------------------------------------------------------------------------------------
 struct GatherBwdPushParams {
     const float* g_cube; const float* g_cabins; const int32_t* idx; const uint16_t* cab_arg;
@@ -450,7 +253,9 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
     const int nbuf = p.nbuf;
     float* acc = gbuf + (p.g_direct ? 0 : (size_t)nbuf * T * RK);                // nbuf * T*N
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();
 
     const long long g_lo = p.rows * blockIdx.x / gridDim.x;
     const long long g_hi = p.rows * (blockIdx.x + 1) / gridDim.x;
@@ -623,14 +428,12 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
         SPK_CUDA(cudaFuncSetAttribute(sp_gather_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = occupancy_slots((const void*)sp_gather_fwd_kernel, G_THREADS, smem, 0);
     grid = std::min<long long>(grid, (p.rows + T - 1) / T);
-    sp_gather_fwd_kernel<<<(int)grid, G_THREADS, smem, (cudaStream_t)stream>>>(p);
-    SPK_LAUNCH_CHECK("sp_gather_fwd_kernel");
+    SPK_CUDA(launch_k(sp_gather_fwd_kernel, dim3((int)grid), dim3(G_THREADS), smem, (cudaStream_t)stream, p));
     if (want_cab && !p.cab_fast) {
         const long long n_rows = (long long)B * C * R;
         const long long total = n_rows * cab;
         const int gsz = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
-        sp_cabins_generic_kernel<<<gsz, 256, 0, (cudaStream_t)stream>>>(sp_cube, k, cab, n_rows, cabins, cab_arg);
-        SPK_LAUNCH_CHECK("sp_cabins_generic_kernel");
+        SPK_CUDA(launch_k(sp_cabins_generic_kernel, dim3(gsz), dim3(256), 0, (cudaStream_t)stream, (const float*)sp_cube, k, cab, n_rows, cabins, cab_arg));
     }
     return SPK_OK;
 }
@@ -663,8 +466,7 @@ static int gather_bwd_push(const float* g_cube, const float* g_cabins, const int
         SPK_CUDA(cudaFuncSetAttribute(sp_gather_bwd_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = occupancy_slots((const void*)sp_gather_bwd_push_kernel, 256, smem, 0);
     grid = std::min<long long>(grid, (p.rows + T - 1) / T);
-    sp_gather_bwd_push_kernel<<<(int)grid, 256, smem, stream>>>(p);
-    SPK_LAUNCH_CHECK("sp_gather_bwd_push_kernel");
+    SPK_CUDA(launch_k(sp_gather_bwd_push_kernel, dim3((int)grid), dim3(256), smem, stream, p));
     return SPK_OK;
 }
 
@@ -682,32 +484,7 @@ extern "C" int sp_gather_bwd_f32(const float* g_cube, const float* g_cabins, con
     }
     if (N > 65536) return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: N=%d > 65536", N);
     if ((long long)B * C >= (1LL << 31)) return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: B*C >= 2^31");
-    const long long RK = (long long)R * k;
-    // rank-bucketed kernel: slot list (u32[RK]) + two gradient tiles + two accumulator tiles in shared memory
-    const size_t budget = (size_t)max_optin_smem();
-    const size_t fixed = 128 + (((size_t)RK * 4 + 127) & ~(size_t)127);
-    const size_t per_T = 2 * ((size_t)RK + (size_t)N) * 4;
-    const size_t scratch = (size_t)RK * 4 + (size_t)N * 2;            // build scratch aliased onto the accumulators
-    if (RK > 65535 || R > 63 || fixed + per_T > budget || 2 * (size_t)N * 4 < scratch)
-        return gather_bwd_push(g_cube, g_cabins, idx, cab_arg, B, C, N, R, k, cab, grad_x, (cudaStream_t)stream);
-    GatherBwdParams p;
-    p.g_cube = g_cube; p.g_cabins = g_cabins; p.idx = idx; p.cab_arg = cab_arg; p.grad_x = grad_x;
-    p.rows = (long long)B * C;
-    p.C = C; p.N = N; p.R = R; p.k = k; p.cab = g_cabins ? cab : 1;
-    p.bulk_in = ((RK & 3) == 0) && (((uintptr_t)g_cube & 15) == 0);
-    p.bulk_out = ((N & 3) == 0) && (((uintptr_t)grad_x & 15) == 0);
-    int T = 8;                                                       // ~72 KB per CTA -> 3 CTAs (24 warps) per SM
-    while (T > 1 && fixed + (size_t)T * per_T > 74 * 1024) T >>= 1;
-    while (T > 1 && T > C) T >>= 1;
-    p.T = T;
-    const size_t smem = fixed + (size_t)T * per_T;
-    if (smem > 48 * 1024)
-        SPK_CUDA(cudaFuncSetAttribute(sp_gather_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long grid = occupancy_slots((const void*)sp_gather_bwd_kernel, G_THREADS, smem, 0);
-    grid = std::min<long long>(grid, (p.rows + T - 1) / T);
-    sp_gather_bwd_kernel<<<(int)grid, G_THREADS, smem, (cudaStream_t)stream>>>(p);
-    SPK_LAUNCH_CHECK("sp_gather_bwd_kernel");
-    return SPK_OK;
+    return gather_bwd_push(g_cube, g_cabins, idx, cab_arg, B, C, N, R, k, cab, grad_x, (cudaStream_t)stream);
 }
 
 extern "C" int sp_cabins_fwd_f32(const float* windows, long long rows, int k, int cab, float* cabins,
@@ -719,8 +496,7 @@ extern "C" int sp_cabins_fwd_f32(const float* windows, long long rows, int k, in
     if (!windows || !cabins || !cab_arg) return fail(SPK_E_BADARG, "sp_cabins_fwd_f32: null pointer");
     const long long total = rows * cab;
     const int g = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
-    sp_cabins_generic_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(windows, k, cab, rows, cabins, cab_arg);
-    SPK_LAUNCH_CHECK("sp_cabins_generic_kernel");
+    SPK_CUDA(launch_k(sp_cabins_generic_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, windows, k, cab, rows, cabins, cab_arg));
     return SPK_OK;
 }
 
@@ -732,7 +508,6 @@ extern "C" int sp_cabins_bwd_f32(const float* g_cabins, const uint16_t* cab_arg,
     if (!g_cabins || !cab_arg || !g_windows) return fail(SPK_E_BADARG, "sp_cabins_bwd_f32: null pointer");
     const long long total = rows * k;
     const int g = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
-    sp_cabins_bwd_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(g_cabins, cab_arg, k, cab, total, g_windows);
-    SPK_LAUNCH_CHECK("sp_cabins_bwd_kernel");
+    SPK_CUDA(launch_k(sp_cabins_bwd_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, g_cabins, cab_arg, k, cab, total, g_windows));
     return SPK_OK;
 }

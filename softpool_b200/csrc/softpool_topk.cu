@@ -72,6 +72,8 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     const int row = blockIdx.x;
     const int b = row / R, r = row - b * R;
     const float* krow = keys + (size_t)row * N;
+    pdl_trigger();
+    pdl_wait();
 #ifdef SPK_TIMING
     long long tq[8]; tq[0] = clock64();
 #define TQ(i) tq[i] = clock64()
@@ -229,6 +231,8 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
 
 __global__ void sp_argmax_kernel(const float* __restrict__ keys, int R, int N,
                                  int64_t* __restrict__ id_activa, long long total) {
+    pdl_trigger();
+    pdl_wait();
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         const long long b = t / N;
@@ -261,8 +265,7 @@ extern "C" int sp_topk_f32(const float* keys, int B, int R, int N, int k, int32_
     const size_t smem = (size_t)K2 * sizeof(uint64_t) + (size_t)E * TOPK_THREADS * sizeof(uint32_t);
     if (smem > 48 * 1024)
         SPK_CUDA(cudaFuncSetAttribute(sp_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sp_topk_kernel<<<B * R, TOPK_THREADS, smem, (cudaStream_t)stream>>>(keys, R, N, k, E, K2, idx, sp_idx, id_activa);
-    SPK_LAUNCH_CHECK("sp_topk_kernel");
+    SPK_CUDA(launch_k(sp_topk_kernel, dim3(B * R), dim3(TOPK_THREADS), smem, (cudaStream_t)stream, keys, R, N, k, E, K2, idx, sp_idx, id_activa));
     return SPK_OK;
 }
 
@@ -273,7 +276,6 @@ extern "C" int sp_argmax_i64(const float* keys, int B, int R, int N, int64_t* id
     if (!keys || !id_activa) return fail(SPK_E_BADARG, "sp_argmax_i64: null pointer");
     const long long total = (long long)B * N;
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
-    sp_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(keys, R, N, id_activa, total);
-    SPK_LAUNCH_CHECK("sp_argmax_kernel");
+    SPK_CUDA(launch_k(sp_argmax_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, keys, R, N, id_activa, total));
     return SPK_OK;
 }

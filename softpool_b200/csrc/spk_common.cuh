@@ -37,6 +37,21 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
                        float* dist2, int32_t* idx1, int32_t* idx2, void* ws, size_t ws_bytes,
                        cudaStream_t st);
 
+bool pdl_enabled();      // SPK_NO_PDL=1 turns programmatic dependent launch off
+
+// Launch with the programmatic-stream-serialization attribute (kernels call pdl_trigger()/pdl_wait()).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // ---- total order of float32 keys -------------------------------------------------------------
@@ -76,11 +91,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra D_%=;\n\t"
         "bra W_%=;\n\t"
         "D_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x4000u)        // suspend-time hint: sleep in hardware instead of spinning
         : "memory");
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
@@ -107,6 +122,15 @@ template <int N>
 __device__ __forceinline__ void bulk_wait() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+
+// ---- programmatic dependent launch (PDL): the next kernel of the stream may start its prologue while this
+// one drains; pdl_wait() blocks until the previous kernel has completed and its writes are visible.
+__device__ __forceinline__ void pdl_trigger() {
+#ifdef SPK_PDL_EARLY_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // streaming 128-bit global store / load
 __device__ __forceinline__ void st_cs_f4(float4* p, float4 v) {

@@ -25,7 +25,8 @@ def init(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                **({"device_id": torch.device("cuda", local_rank)} if backend == "nccl" else {}))
     return rank, local_rank, world
 
 
