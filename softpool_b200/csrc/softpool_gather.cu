@@ -454,7 +454,8 @@ static int gather_bwd_push(const float* g_cube, const float* g_cabins, const int
     size_t per_T = 2 * ((size_t)N + (size_t)RK) * 4;                // double-buffered acc + g per row
     p.k_shift = ilog2_exact(k);
     p.nbuf = 2; p.g_direct = 0;
-    if (fixed + per_T > budget) { per_T /= 2; p.nbuf = 1; }
+    // prefer two resident CTAs per SM over double buffering inside one
+    if (fixed + per_T > budget || (fixed + per_T > 110 * 1024 && fixed + per_T / 2 <= 110 * 1024)) { per_T /= 2; p.nbuf = 1; }
     if (fixed + per_T > budget) { per_T = (size_t)N * 4; p.g_direct = 1; }
     if (fixed + per_T > budget)
         return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: N=%d, R*k=%lld do not fit shared memory", N, RK);
