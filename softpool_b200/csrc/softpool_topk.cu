@@ -66,7 +66,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);                 // K2 survivors
     uint32_t* sk = reinterpret_cast<uint32_t*>(sel + K2);                  // E*256 keys, [e][t]
-    __shared__ int hist[3][TOPK_THREADS / 32][16];
+    int* hist = reinterpret_cast<int*>(sk + (size_t)E * TOPK_THREADS);     // 3 x 8 warps x 16 bins
     __shared__ int warp_tot[TOPK_THREADS / 32];
     const int tid = threadIdx.x;
     const int row = blockIdx.x;
@@ -115,7 +115,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         }
     }
     for (int i = tid; i < K2; i += TOPK_THREADS) sel[i] = 0ull;
-    for (int i = tid; i < 3 * 8 * 16; i += TOPK_THREADS) (&hist[0][0][0])[i] = 0;
+    for (int i = tid; i < 3 * 8 * 16; i += TOPK_THREADS) hist[i] = 0;
 
     // ---- argmax over the R rows for this CTA's slice of n (softpool.py:95) --------------------------
     if (id_activa != nullptr) {
@@ -140,12 +140,13 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     // ---- 2. radix select of the k-th largest key, 4 bits per round ---------------------------------------
     // Warp-private 16-bin histograms of the keys that still match the decided prefix (shared-memory
     // atomics), one barrier per round; every warp then reduces the 8 histograms itself.
+    // (8-bit digits / 256-bin histograms: measured slower, 17.4 vs 12.5 us at N=2048.)
     uint32_t V = 0;
     int want = k;                                        // rank still to be located inside the prefix bucket
     const int lane = tid & 31, warp = tid >> 5;
     for (int round = 0; round < 8; ++round) {
         const int sh = 28 - 4 * round;
-        int* H = &hist[round % 3][0][0];
+        int* H = hist + (round % 3) * (8 * 16);
         const uint32_t pre = (round == 0) ? 0u : (V >> (sh + 4));
 #pragma unroll 4
         for (int e = 0; e < E; ++e) {
@@ -172,7 +173,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         want -= above;
         V |= (uint32_t)dsel << sh;
         // recycle the histogram used two rounds from now (everybody is past the barrier of the previous round)
-        int* Hz = &hist[(round + 2) % 3][0][0];
+        int* Hz = hist + ((round + 2) % 3) * (8 * 16);
         if (tid < 8 * 16) Hz[tid] = 0;
     }
 
@@ -184,9 +185,10 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         const uint32_t key = sk[e * TOPK_THREADS + tid];
         my_gt += key > V; my_eq += key == V;
     }
-    int total_gt, total_eq;
-    const int eq_before = block_exclusive_scan(my_eq, warp_tot, tid, total_eq);
-    (void)block_exclusive_scan(my_gt, warp_tot, tid, total_gt);
+    // one scan for both counts: (gt << 16) | eq  (each <= E*256 <= 16384)
+    int total_ge;
+    const int ge_before = block_exclusive_scan((my_gt << 16) | my_eq, warp_tot, tid, total_ge);
+    const int eq_before = ge_before & 0xFFFF, total_gt = total_ge >> 16;
     const int need = k - total_gt;                       // >= 1 ties to take, lowest indices first
     const int my_eq_taken = max(0, min(my_eq, need - eq_before));
     int total_sel;
@@ -201,13 +203,29 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
 
     TQ(3);
     // ---- 4. sort the survivors (descending; unique words => stable order) ---------------------------------
-    int prev = 64;
-    for (int size = 2; size <= K2; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            stage_sync(stride, prev);
-            ce_stage(sel, K2, size, stride, tid, TOPK_THREADS);
-            prev = stride;
+    if (K2 <= 32) {
+        // one warp, one word per lane, bitonic network on shuffles: no barriers
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t v = (lane < K2) ? sel[lane] : 0ull;
+            for (int size = 2; size <= K2; size <<= 1)
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, v, stride);
+                    const bool desc = (lane & size) == 0 || size == K2;
+                    const bool lower = (lane & stride) == 0;          // this lane keeps the first of the pair
+                    v = (lower == desc) ? (o > v ? o : v) : (o < v ? o : v);
+                }
+            if (lane < K2) sel[lane] = v;
         }
+    } else {
+        int prev = 64;
+        for (int size = 2; size <= K2; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                stage_sync(stride, prev);
+                ce_stage(sel, K2, size, stride, tid, TOPK_THREADS);
+                prev = stride;
+            }
+    }
     __syncthreads();
     TQ(4);
 
@@ -262,7 +280,7 @@ extern "C" int sp_topk_f32(const float* keys, int B, int R, int N, int k, int32_
     const int K2 = max(2, next_pow2(k));
     int E = (N + TOPK_THREADS - 1) / TOPK_THREADS;
     if (E > 4) E = (E + 3) & ~3;                       // float4 path wants E % 4 == 0
-    const size_t smem = (size_t)K2 * sizeof(uint64_t) + (size_t)E * TOPK_THREADS * sizeof(uint32_t);
+    const size_t smem = (size_t)K2 * sizeof(uint64_t) + (size_t)E * TOPK_THREADS * sizeof(uint32_t) + 3 * 8 * 16 * sizeof(int);
     if (smem > 48 * 1024)
         SPK_CUDA(cudaFuncSetAttribute(sp_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPK_CUDA(launch_k(sp_topk_kernel, dim3(B * R), dim3(TOPK_THREADS), smem, (cudaStream_t)stream, keys, R, N, k, E, K2, idx, sp_idx, id_activa));
