@@ -145,7 +145,7 @@ class BufferSet:
 
 
 KERNELS = ["sp_topk_f32", "sp_gather_fwd_f32", "sp_gather_bwd_f32", "chamfer_fwd_f32", "chamfer_loss_f32", "chamfer_bwd_f32"]
-LAUNCHES_PER_STEP = 7     # chamfer_bwd_f32 is two kernels (direct + scatter)
+LAUNCHES_PER_STEP = 8     # chamfer_fwd_f32 = prep + tensor kernel, chamfer_bwd_f32 = direct + scatter
 
 
 class Step:

@@ -15,6 +15,7 @@
 //     bulk store (cp.async.bulk.global.shared::cta) while the next tile is accumulated in the other
 //     buffer.  grad_x is fully overwritten (zeros included): no memset.
 #include "spk_common.cuh"
+#include <stdlib.h>
 
 namespace spk {
 
@@ -251,7 +252,8 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
     uint16_t* idx_s = reinterpret_cast<uint16_t*>(smem_raw + 128);               // RK
     float* gbuf = reinterpret_cast<float*>(smem_raw + 128 + ((RK * 2 + 127) & ~127));   // 2 * T*RK
     const int nbuf = p.nbuf;
-    float* acc = gbuf + (p.g_direct ? 0 : (size_t)nbuf * T * RK);                // nbuf * T*N
+    const size_t gstride = ((size_t)T * RK + 3) & ~(size_t)3, astride = ((size_t)T * N + 3) & ~(size_t)3;   // 16-byte multiples
+    float* acc = gbuf + (p.g_direct ? 0 : (size_t)nbuf * gstride);               // nbuf * T*N
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
     pdl_trigger();
     __syncthreads();
@@ -274,7 +276,7 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
         if (p.bulk_in && !p.g_direct) {
             const uint32_t bytes = (uint32_t)rows * RK * 4u;
             mbar_expect_tx(&bars[buf], bytes);
-            bulk_g2s(gbuf + (size_t)buf * T * RK, p.g_cube + (size_t)g * RK, bytes, &bars[buf]);
+            bulk_g2s(gbuf + (size_t)buf * gstride, p.g_cube + (size_t)g * RK, bytes, &bars[buf]);
         }
     };
 
@@ -285,8 +287,8 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
         const int buf = (nbuf == 2) ? (gi & 1) : 0;
         const int rows = group_rows(g);
         const long long g_next = g + rows;
-        float* gs = gbuf + (size_t)buf * T * RK;
-        float* ac = acc + (size_t)buf * T * N;
+        float* gs = gbuf + (size_t)buf * gstride;
+        float* ac = acc + (size_t)buf * astride;
         // prefetch the next group's upstream gradient into the other buffer (its previous reader,
         // group gi-1, finished before the barrier that ended that iteration)
         if (nbuf == 2 && g_next < g_hi && tid == 0) issue_load(g_next, group_rows(g_next), buf ^ 1);
@@ -457,12 +459,14 @@ static int gather_bwd_push(const float* g_cube, const float* g_cabins, const int
     // prefer two resident CTAs per SM over double buffering inside one
     if (fixed + per_T > budget || (fixed + per_T > 110 * 1024 && fixed + per_T / 2 <= 110 * 1024)) { per_T /= 2; p.nbuf = 1; }
     if (fixed + per_T > budget) { per_T = (size_t)N * 4; p.g_direct = 1; }
-    if (fixed + per_T > budget)
+    if (fixed + per_T + 64 > budget)
         return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: N=%d, R*k=%lld do not fit shared memory", N, RK);
-    int T = (int)std::max<size_t>(1, std::min<size_t>(8, (72 * 1024 - std::min<size_t>(fixed, 72 * 1024)) / per_T));
+    size_t target = 72 * 1024;
+    if (const char* e = getenv("SPK_BWD_SMEM_KB")) target = (size_t)atoi(e) * 1024;      // tuning knob
+    int T = (int)std::max<size_t>(1, std::min<size_t>(8, (target - std::min<size_t>(fixed, target)) / per_T));
     T = std::min(T, C);
     p.T = T;
-    const size_t smem = fixed + (size_t)T * per_T;
+    const size_t smem = fixed + (size_t)T * per_T + 64;             // + padding of the buffer strides to 16 bytes
     if (smem > 48 * 1024)
         SPK_CUDA(cudaFuncSetAttribute(sp_gather_bwd_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = occupancy_slots((const void*)sp_gather_bwd_push_kernel, 256, smem, 0);

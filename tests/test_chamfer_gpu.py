@@ -245,3 +245,18 @@ def test_non_finite_inputs_do_not_hang():
     ok = np.ones(400, bool); ok[3] = False
     r = co.forward(a[1:], b[1:])           # sample 1 has an inf coordinate but no NaN: still comparable
     assert np.array_equal(i1[1], r[2][0])
+
+
+def test_random_shapes_vs_oracle():
+    """40 random cloud sizes on both sides of the tensor-path threshold, ragged against the 128/1024 tiling."""
+    rng = np.random.default_rng(77)
+    for trial in range(40):
+        B = int(rng.integers(1, 5)); n = int(rng.integers(1, 1500)); m = int(rng.integers(1, 2600))
+        a, b = clouds(B, n, m, seed=1000 + trial, scale=float(rng.choice([1.0, 0.01, 37.0])))
+        if trial % 4 == 0:
+            b[:, : min(m, 50)] = a[:, :1]               # many exact ties at distance 0 for the first query
+        r = co.forward(a, b)
+        o = cuda_forward(a, b)
+        tag = "trial %d: B=%d n=%d m=%d" % (trial, B, n, m)
+        for x, y in zip(o, r):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), tag

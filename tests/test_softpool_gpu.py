@@ -248,3 +248,48 @@ def test_errors_are_loud():
         ops.softpool_topk(torch.randn(1, 1, 20000, device=dev()), 4)     # N > 16384 unsupported
     with pytest.raises(RuntimeError):
         ops.softpool_gather(torch.randn(1, 2, 8, device=dev()), torch.zeros(1, 1, 4, dtype=torch.int32, device=dev()), 5)
+
+
+def test_random_shapes_vs_oracle():
+    """60 random small shapes (ragged everything: tiles crossing sample boundaries, k not multiple of 4,
+    windows with trailing slots, C smaller than a tile, R*k > N): bit-exact against the oracle."""
+    rng = np.random.default_rng(20261017)
+    for trial in range(60):
+        B = int(rng.integers(1, 6)); C = int(rng.integers(1, 41)); N = int(rng.integers(1, 700))
+        R = int(rng.integers(1, 10)); k = int(rng.integers(1, N + 1)); cab = int(rng.integers(1, min(k, 9) + 1))
+        if trial % 3 == 0:                       # the aligned fast paths, too
+            N = int(rng.choice([64, 128, 256, 512, 1024])); k = int(rng.choice([8, 16, 32, 64])); k = min(k, N)
+            cab = int(rng.choice([1, 2, 4, 8])); cab = min(cab, k)
+        x = rng.standard_normal((B, C, N), dtype=np.float32)
+        keys = rng.standard_normal((B, R, N), dtype=np.float32)
+        if trial % 2:
+            keys = np.round(keys * 4) / 4; x = np.round(x * 4) / 4
+        g_cube = rng.standard_normal((B, C, R, k), dtype=np.float32)
+        g_cabins = rng.standard_normal((B, C, R, cab), dtype=np.float32)
+        ref = so.softpool_forward(x, keys, k, cab)
+        ref_grad = so.softpool_backward(g_cube, g_cabins, ref["idx"], ref["cab_arg"], N)
+        out = run_cuda(x, keys, k, cab, g_cube, g_cabins)
+        tag = "trial %d: B=%d C=%d N=%d R=%d k=%d cab=%d" % (trial, B, C, N, R, k, cab)
+        assert np.array_equal(out["idx"], ref["idx"]), tag
+        assert np.array_equal(out["sp_idx"], ref["sp_idx"]), tag
+        assert np.array_equal(out["id_activa"], ref["id_activa"]), tag
+        assert np.array_equal(bits(out["sp_cube"]), bits(ref["sp_cube"])), tag
+        assert np.array_equal(bits(out["cabins"]), bits(ref["cabins"])), tag
+        assert np.array_equal(bits(out["grad_x"]), bits(ref_grad)), tag
+
+
+def test_backward_is_deterministic_and_without_cabins_grad():
+    from softpool_b200 import ops
+    torch.manual_seed(3)
+    x = torch.randn(4, 64, 2048, device=dev(), requires_grad=True)
+    keys = torch.randn(4, 8, 2048, device=dev())
+    idx, _, _ = ops.softpool_topk(keys, 256)
+    g = torch.randn(4, 64, 8, 256, device=dev())
+    outs = []
+    for _ in range(3):
+        cube, cab = ops.softpool_gather(x, idx, 8)
+        (gx,) = torch.autograd.grad(cube, x, g)               # cabins unused: its gradient is None
+        outs.append(gx)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    ref = torch.zeros_like(x).scatter_add_(2, idx.long().reshape(4, 1, -1).expand(4, 64, -1), g.reshape(4, 64, -1))
+    torch.testing.assert_close(outs[0], ref, rtol=1e-4, atol=1e-5)
