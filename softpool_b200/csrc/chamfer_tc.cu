@@ -394,8 +394,11 @@ chamfer_tc_kernel(const TcParams p) {
             const float tau = p.meta[b].tau, scale2 = p.meta[b].scale2;
             float qx = 0.f, qy = 0.f, qz = 0.f;
             if (live) { qx = __ldg(Qx + 3 * (size_t)gq); qy = __ldg(Qx + 3 * (size_t)gq + 1); qz = __ldg(Qx + 3 * (size_t)gq + 2); }
-            // reference: the first target initialises the running best (`k==0 || d<best`, chamfer.cu:36)
-            float best_d = ref_sqdist_tc(qx, qy, qz, __ldg(Tx), __ldg(Tx + 1), __ldg(Tx + 2));
+            // reference: the first target initialises the running best (`k==0 || d<best`, chamfer.cu:36).
+            // The loads are issued here, the distance is formed at the first filter: their latency hides
+            // behind the first super-block's min pass.
+            const float t0x = __ldg(Tx), t0y = __ldg(Tx + 1), t0z = __ldg(Tx + 2);
+            float best_d = 0.f;
             int best_i = 0;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * (TC_N / 2);
 
@@ -434,6 +437,7 @@ chamfer_tc_kernel(const TcParams p) {
                 S.rowmin[sb & 1][h][row] = rmin;
                 epi_bar();
                 rmin = fminf(rmin, S.rowmin[sb & 1][h ^ 1][row]);
+                if (sb == 0) best_d = ref_sqdist_tc(qx, qy, qz, t0x, t0y, t0z);
                 float thr = fminf(rmin, best_d * scale2) + tau;
                 if (!(thr == thr)) thr = INFINITY;                       // NaN anywhere: evaluate everything
                 uint32_t mask = 0;
