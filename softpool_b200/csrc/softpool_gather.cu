@@ -236,6 +236,7 @@ struct GatherBwdPushParams {
     int nbuf;         // 2 = double-buffered acc/g (default), 1 = single (rows too large for two)
     int g_direct;     // 1 = upstream gradient read straight from global (R*k too large to stage)
     int k_shift;      // log2(k) when k is a power of two, else -1
+    int ng;           // gradient ring depth (2..4) when nbuf == 2: tiles are fetched ng-1 groups ahead
 };
 
 // Each CTA owns a contiguous range of global rows and walks it in groups of <= T rows that lie in
@@ -252,9 +253,10 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
     uint16_t* idx_s = reinterpret_cast<uint16_t*>(smem_raw + 128);               // RK
     float* gbuf = reinterpret_cast<float*>(smem_raw + 128 + ((RK * 2 + 127) & ~127));   // 2 * T*RK
     const int nbuf = p.nbuf;
+    const int NG = (nbuf == 2) ? p.ng : 1;                                       // gradient ring depth
     const size_t gstride = ((size_t)T * RK + 3) & ~(size_t)3, astride = ((size_t)T * N + 3) & ~(size_t)3;   // 16-byte multiples
-    float* acc = gbuf + (p.g_direct ? 0 : (size_t)nbuf * gstride);               // nbuf * T*N
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    float* acc = gbuf + (p.g_direct ? 0 : (size_t)NG * gstride);                 // nbuf * T*N
+    if (tid == 0) { for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
     pdl_trigger();
     __syncthreads();
     pdl_wait();
@@ -265,13 +267,7 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
     const int wins = R * p.cab;
 
     // group i covers rows [g, g + rows_i): never crosses a sample boundary
-    auto group_rows = [&](long long g) -> int {
-        const long long in_sample = (long long)C - (g % C);
-        long long r = g_hi - g;
-        if (r > T) r = T;
-        if (r > in_sample) r = in_sample;
-        return (int)r;
-    };
+    auto group_rows = [&](long long g) -> int { return tile_rows(g, g_hi, T, C); };
     auto issue_load = [&](long long g, int rows, int buf) {        // tid 0 only
         if (p.bulk_in && !p.g_direct) {
             const uint32_t bytes = (uint32_t)rows * RK * 4u;
@@ -280,21 +276,31 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
         }
     };
 
-    long long g = g_lo;
-    int cur_b = -1;
-    if (g < g_hi && tid == 0) issue_load(g, group_rows(g), 0);
+    long long g = g_lo, g_pref = g_lo;
+    int cur_b = -1, gi_pref = 0;
+    // prologue: the first NG-1 gradient tiles (single-buffered: just the first)
+    for (; gi_pref < (NG > 1 ? NG - 1 : 1) && g_pref < g_hi; ++gi_pref) {
+        const int r = group_rows(g_pref);
+        if (tid == 0) issue_load(g_pref, r, gi_pref % NG);
+        g_pref += r;
+    }
     for (int gi = 0; g < g_hi; ++gi) {
         const int buf = (nbuf == 2) ? (gi & 1) : 0;
+        const int gslot = gi % NG;
         const int rows = group_rows(g);
         const long long g_next = g + rows;
-        float* gs = gbuf + (size_t)buf * gstride;
+        float* gs = gbuf + (size_t)gslot * gstride;
         float* ac = acc + (size_t)buf * astride;
-        // prefetch the next group's upstream gradient into the other buffer (its previous reader,
-        // group gi-1, finished before the barrier that ended that iteration)
-        if (nbuf == 2 && g_next < g_hi && tid == 0) issue_load(g_next, group_rows(g_next), buf ^ 1);
+        // keep NG-1 gradient tiles in flight: the slot refilled here was consumed by group gi-1, whose
+        // readers finished before the barrier that ended that iteration
+        if (NG > 1 && g_pref < g_hi) {
+            const int r = group_rows(g_pref);
+            if (tid == 0) issue_load(g_pref, r, gi_pref % NG);
+            g_pref += r; ++gi_pref;
+        }
         // acc[buf] was handed to the TMA store nbuf groups ago: wait until that store has READ it
         if (p.bulk_out && tid == 0) { if (nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
-        const int b = (int)(g / C);
+        const int b = (int)((unsigned)g / (unsigned)C);
         if (b != cur_b) {                                            // new sample: its index list
             __syncthreads();
             const int32_t* ib = p.idx + (size_t)b * RK;
@@ -311,7 +317,7 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
         if (p.g_direct) {
             // nothing staged
         } else if (p.bulk_in) {
-            mbar_wait(&bars[buf], (uint32_t)((nbuf == 2 ? (gi >> 1) : gi) & 1));
+            mbar_wait(&bars[gslot], (uint32_t)((gi / NG) & 1));
         } else {
             const float* src = p.g_cube + (size_t)g * RK;
             for (int i = tid; i < rows * RK; i += nthr) gs[i] = __ldg(src + i);
@@ -364,7 +370,11 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
             __syncthreads();
         }
         // single-buffered: the next group's gradient can only be fetched once this one is consumed
-        if (nbuf == 1 && g_next < g_hi && tid == 0) issue_load(g_next, group_rows(g_next), 0);
+        if (NG == 1 && g_pref < g_hi) {
+            const int r = group_rows(g_pref);
+            if (tid == 0) issue_load(g_pref, r, 0);
+            g_pref += r; ++gi_pref;
+        }
         g = g_next;
     }
     if (p.bulk_out && tid == 0) bulk_wait<0>();
@@ -461,12 +471,21 @@ static int gather_bwd_push(const float* g_cube, const float* g_cabins, const int
     if (fixed + per_T > budget) { per_T = (size_t)N * 4; p.g_direct = 1; }
     if (fixed + per_T + 64 > budget)
         return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: N=%d, R*k=%lld do not fit shared memory", N, RK);
+    p.ng = 2;
     size_t target = 72 * 1024;
     if (const char* e = getenv("SPK_BWD_SMEM_KB")) target = (size_t)atoi(e) * 1024;      // tuning knob
     int T = (int)std::max<size_t>(1, std::min<size_t>(8, (target - std::min<size_t>(fixed, target)) / per_T));
     T = std::min(T, C);
     p.T = T;
-    const size_t smem = fixed + (size_t)T * per_T + 64;             // + padding of the buffer strides to 16 bytes
+    size_t smem = fixed + (size_t)T * per_T + 64;                   // + padding of the buffer strides to 16 bytes
+    if (p.nbuf == 2 && !p.g_direct) {                               // deeper gradient ring while it fits the same budget
+        const size_t gtile = (((size_t)T * RK + 3) & ~(size_t)3) * 4;
+        // measured on B200: a deeper ring (3-4 tiles in flight) is SLOWER at config A (28.0 vs 23.5 us), so the
+        // default stays at 2; SPK_BWD_RING=3|4 re-enables it for experiments
+        int want = 2;
+        if (const char* e = getenv("SPK_BWD_RING")) want = std::max(2, std::min(4, atoi(e)));
+        while (p.ng < want && smem + gtile <= std::max(target, (size_t)74 * 1024)) { smem += gtile; ++p.ng; }
+    }
     if (smem > 48 * 1024)
         SPK_CUDA(cudaFuncSetAttribute(sp_gather_bwd_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = occupancy_slots((const void*)sp_gather_bwd_push_kernel, 256, smem, 0);
