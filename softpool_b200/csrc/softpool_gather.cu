@@ -380,6 +380,248 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
     if (p.bulk_out && tid == 0) bulk_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward, "pull" formulation: no shared-memory accumulator, no zero fill, no per-region barriers.
+// Per sample the CTA builds an inverse table once (shared by all C rows of the sample):
+//   first[n]   = slot (r*k+j) of the LOWEST region that selected point n, or NONE
+//   link[slot] = slot of the next higher region that selected the same point, or NONE
+// (built in descending region order by prepending; points are unique inside a region, so one
+// region per phase needs no atomics).  Then every thread owns 4 consecutive points of T rows:
+// it walks the (mostly 0- or 1-element) chains, sums the staged upstream gradient in ascending
+// region order (same order as the push kernel and the oracle) and writes the finished values
+// with one 128-bit streaming store per row -- grad_x is written exactly once, straight from
+// registers.  The gradient tiles arrive by bulk copy through a ring, the window-max gradient
+// is folded into the winning slot of the staged tile.
+// ---------------------------------------------------------------------------------------------
+struct GatherBwdPullParams {
+    const float* g_cube; const float* g_cabins; const int32_t* idx; const uint16_t* cab_arg;
+    float* grad_x;
+    long long rows;   // B*C
+    int C, N, R, k, cab;
+    int bulk_in;      // (R*k)%4==0 and g_cube 16B aligned -> g rows arrive with cp.async.bulk
+    int cab_bulk;     // window-max gradient + arg-max ride along with the tile (bulk copies)
+    int vec_out;      // N%4==0 and grad_x 16B aligned -> 128-bit stores
+    int ng;           // ring depth (>= 2)
+    int dbg;          // timing experiments only (results wrong): 1 no table build, 2 no window-max fold, 4 no gradient tiles
+};
+
+constexpr uint32_t PULL_NONE = 0xFFFFu;
+
+// bytes of one ring slot: gradient tile + (optionally) the group's g_cabins (f32) and cab_arg (u16)
+static __host__ __device__ inline size_t pull_slot_bytes(int T, int RK, int wins, bool cab_bulk) {
+    size_t b = (((size_t)T * RK + 3) & ~(size_t)3) * 4;
+    if (cab_bulk) b += (size_t)T * wins * 4 + (((size_t)T * wins * 2 + 15) & ~(size_t)15);
+    return b;
+}
+
+template <int T, int NT>
+__global__ void __launch_bounds__(NT)
+sp_gather_bwd_pull_kernel(const GatherBwdPullParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    constexpr int nthr = NT;
+    const int N = p.N, R = p.R, k = p.k, C = p.C;
+    const int RK = R * k;
+    const int NG = p.ng;
+    const bool has_cab = p.g_cabins != nullptr && !(p.dbg & 2);
+    const int wl = has_cab ? k / p.cab : 1;
+    const int wins = R * p.cab;
+    const bool cab_bulk = has_cab && p.cab_bulk;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                              // <= 8
+    uint16_t* first = reinterpret_cast<uint16_t*>(smem_raw + 128);                       // N (padded to 4)
+    const size_t first_bytes = ((((size_t)N + 3) & ~(size_t)3) * 2 + 127) & ~(size_t)127;
+    uint16_t* link = reinterpret_cast<uint16_t*>(smem_raw + 128 + first_bytes);          // RK
+    const size_t link_bytes = ((size_t)RK * 2 + 127) & ~(size_t)127;
+    unsigned char* ring = smem_raw + 128 + first_bytes + link_bytes;                     // NG slots
+    const size_t slot_bytes = pull_slot_bytes(T, RK, wins, p.cab_bulk && p.g_cabins != nullptr);
+    const size_t tile_bytes = (((size_t)T * RK + 3) & ~(size_t)3) * 4;
+    if (tid == 0) { for (int i = 0; i < NG; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
+    pdl_trigger();
+    __syncthreads();
+    pdl_wait();
+
+    const long long g_lo = p.rows * blockIdx.x / gridDim.x;
+    const long long g_hi = p.rows * (blockIdx.x + 1) / gridDim.x;
+
+    auto group_rows = [&](long long g) -> int { return tile_rows(g, g_hi, T, C); };
+    auto issue_load = [&](long long g, int rows, int slot) {       // tid 0 only
+        unsigned char* sl = ring + (size_t)slot * slot_bytes;
+        uint32_t bytes = 0;
+        const uint32_t gb = (uint32_t)rows * RK * 4u, cb = (uint32_t)rows * wins * 4u, ab = (uint32_t)rows * wins * 2u;
+        if (p.bulk_in && !(p.dbg & 4)) bytes += gb;
+        if (cab_bulk) bytes += cb + ab;
+        if (bytes == 0) return;
+        mbar_expect_tx(&bars[slot], bytes);
+        if (p.bulk_in && !(p.dbg & 4)) bulk_g2s(sl, p.g_cube + (size_t)g * RK, gb, &bars[slot]);
+        if (cab_bulk) {
+            bulk_g2s(sl + tile_bytes, p.g_cabins + (size_t)g * wins, cb, &bars[slot]);
+            bulk_g2s(sl + tile_bytes + (size_t)T * wins * 4, p.cab_arg + (size_t)g * wins, ab, &bars[slot]);
+        }
+    };
+    const bool any_bulk = (p.bulk_in && !(p.dbg & 4)) || cab_bulk;
+
+    // destination (inside the staged tile, before the arg-max offset) of the window-max terms this
+    // thread folds: entries e = tid and tid + nthr of the group's rows*wins list -- group-invariant
+    int cbase[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int e = tid + u * nthr;
+        const int t = e / wins, rw = e - t * wins;
+        const int r = rw / p.cab, w = rw - r * p.cab;
+        cbase[u] = t * RK + r * k + w * wl;
+    }
+
+    long long g = g_lo, g_pref = g_lo;
+    int cur_b = -1, gi_pref = 0;
+    for (; gi_pref < NG - 1 && g_pref < g_hi; ++gi_pref) {
+        const int r = group_rows(g_pref);
+        if (tid == 0) issue_load(g_pref, r, gi_pref % NG);
+        g_pref += r;
+    }
+    for (int gi = 0; g < g_hi; ++gi) {
+        const int gslot = gi % NG;
+        const int rows = group_rows(g);
+        unsigned char* sl = ring + (size_t)gslot * slot_bytes;
+        float* gs = reinterpret_cast<float*>(sl);
+        // keep NG-1 groups in flight: the slot refilled here was consumed by group gi-1, whose readers
+        // passed the barrier that ended that iteration
+        if (g_pref < g_hi) {
+            const int r = group_rows(g_pref);
+            if (tid == 0) issue_load(g_pref, r, gi_pref % NG);
+            g_pref += r; ++gi_pref;
+        }
+        // window-max gradient without the bulk path: fetched now, folded once the tile has landed
+        float cg[2] = {0.f, 0.f}; int coff[2] = {-1, -1};
+        if (has_cab && !cab_bulk) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + u * nthr;
+                if (e < rows * wins) {
+                    const size_t o = (size_t)g * wins + e;
+                    coff[u] = (int)__ldg(p.cab_arg + o);
+                    cg[u] = __ldg(p.g_cabins + o);
+                }
+            }
+        }
+        const int b = (int)((unsigned)g / (unsigned)C);
+        if (b != cur_b) {                                          // new sample: rebuild the inverse table
+            cur_b = b;                                             // (readers of the old one passed the last barrier)
+            const int32_t* ib = p.idx + (size_t)b * RK;
+            for (int i = tid; i < RK; i += nthr) link[i] = (uint16_t)__ldg(ib + i);
+            {
+                uint2* f2 = reinterpret_cast<uint2*>(first);
+                for (int i = tid; i < ((N + 3) >> 2); i += nthr) f2[i] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+            }
+            __syncthreads();
+            for (int r = (p.dbg & 1) ? -1 : R - 1; r >= 0; --r) {  // descending: chains come out ascending
+                for (int j = tid; j < k; j += nthr) {
+                    const int s = r * k + j;
+                    const int n = link[s];                         // still the point index of slot s
+                    link[s] = first[n];
+                    first[n] = (uint16_t)s;
+                }
+                __syncthreads();
+            }
+        }
+        if (any_bulk) mbar_wait(&bars[gslot], (uint32_t)((gi / NG) & 1));
+        if (!p.bulk_in && !(p.dbg & 4)) {
+            const float* src = p.g_cube + (size_t)g * RK;
+            for (int i = tid; i < rows * RK; i += nthr) gs[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        if (has_cab) {                                             // unique destinations: plain adds
+            if (cab_bulk) {
+                const float* cgs = reinterpret_cast<const float*>(sl + tile_bytes);
+                const uint16_t* cas = reinterpret_cast<const uint16_t*>(sl + tile_bytes + (size_t)T * wins * 4);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int e = tid + u * nthr;
+                    if (e < rows * wins) gs[cbase[u] + (int)cas[e]] += cgs[e];
+                }
+                for (int e = tid + 2 * nthr; e < rows * wins; e += nthr) {
+                    const int t = e / wins, rw = e - t * wins;
+                    const int r = rw / p.cab, w = rw - r * p.cab;
+                    gs[t * RK + r * k + w * wl + (int)cas[e]] += cgs[e];
+                }
+            } else {
+                if (coff[0] >= 0) gs[cbase[0] + coff[0]] += cg[0];
+                if (coff[1] >= 0) gs[cbase[1] + coff[1]] += cg[1];
+                for (int e = tid + 2 * nthr; e < rows * wins; e += nthr) {
+                    const int t = e / wins, rw = e - t * wins;
+                    const int r = rw / p.cab, w = rw - r * p.cab;
+                    const size_t o = (size_t)g * wins + e;
+                    gs[t * RK + r * k + w * wl + (int)__ldg(p.cab_arg + o)] += __ldg(p.g_cabins + o);
+                }
+            }
+            __syncthreads();
+        }
+        float* dst = p.grad_x + (size_t)g * N;
+        if (p.vec_out) {
+            const int NQ = N >> 2;
+            for (int q = tid; q < NQ; q += nthr) {
+                const uint2 f = *reinterpret_cast<const uint2*>(first + 4 * q);
+                float acc[4][T];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int t = 0; t < T; ++t) acc[c][t] = 0.f;
+                if ((f.x & f.y) != 0xFFFFFFFFu) {                  // at least one of the 4 points was selected
+                    const uint32_t s4[4] = {f.x & 0xFFFFu, f.x >> 16, f.y & 0xFFFFu, f.y >> 16};
+                    uint32_t nx[4];
+                    // lowest region of every point: straight-line, all loads independent (slot 0 stands in
+                    // for "none" so that nothing is predicated)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const bool on = s4[c] != PULL_NONE;
+                        const uint32_t sc = on ? s4[c] : 0u;
+                        const uint32_t l = link[sc];
+                        nx[c] = on ? l : PULL_NONE;
+#pragma unroll
+                        for (int t = 0; t < T; ++t) {              // rows beyond `rows` read stale tile bytes: never stored
+                            const float v = gs[t * RK + sc];
+                            acc[c][t] = on ? 0.f + v : 0.f;        // 0 + v: the oracle's accumulator starts at +0
+                        }
+                    }
+                    // points selected by more than one region (rare): ascending regions, in lockstep
+                    while ((nx[0] & nx[1] & nx[2] & nx[3]) != PULL_NONE) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (nx[c] != PULL_NONE) {
+#pragma unroll
+                                for (int t = 0; t < T; ++t) acc[c][t] += gs[t * RK + nx[c]];
+                                nx[c] = link[nx[c]];
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                    if (t < rows)
+                        st_cs_f4(reinterpret_cast<float4*>(dst + (size_t)t * N) + q,
+                                 make_float4(acc[0][t], acc[1][t], acc[2][t], acc[3][t]));
+            }
+        } else {
+            for (int n = tid; n < N; n += nthr) {
+                float acc[T];
+#pragma unroll
+                for (int t = 0; t < T; ++t) acc[t] = 0.f;
+                uint32_t s = first[n];
+                while (s != PULL_NONE) {
+#pragma unroll
+                    for (int t = 0; t < T; ++t) acc[t] += gs[t * RK + s];
+                    s = link[s];
+                }
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                    if (t < rows) dst[(size_t)t * N + n] = acc[t];
+            }
+        }
+        if (has_cab) fence_proxy_async_smem();                     // the fold wrote gs with generic stores; TMA refills it
+        __syncthreads();                                           // the slot and the table are free again
+        g += rows;
+    }
+}
+
 }  // namespace spk
 
 static int occupancy_slots(const void* kernel, int threads, size_t smem, int cap_per_sm) {
@@ -494,6 +736,83 @@ static int gather_bwd_push(const float* g_cube, const float* g_cabins, const int
     return SPK_OK;
 }
 
+
+template <int T, int NT>
+static int launch_pull(const spk::GatherBwdPullParams& p, size_t smem, cudaStream_t stream) {
+    using namespace spk;
+    if (smem > 48 * 1024)
+        SPK_CUDA(cudaFuncSetAttribute(sp_gather_bwd_pull_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = occupancy_slots((const void*)sp_gather_bwd_pull_kernel<T, NT>, NT, smem, 0);
+    grid = std::min<long long>(grid, (p.rows + T - 1) / T);
+    SPK_CUDA(launch_k(sp_gather_bwd_pull_kernel<T, NT>, dim3((int)grid), dim3(NT), smem, stream, p));
+    return SPK_OK;
+}
+
+// returns 1 when the sizes do not suit the pull kernel (caller falls back to the push kernel)
+static int gather_bwd_pull(const float* g_cube, const float* g_cabins, const int32_t* idx,
+                           const uint16_t* cab_arg, int B, int C, int N, int R, int k, int cab,
+                           float* grad_x, cudaStream_t stream) {
+    using namespace spk;
+    const long long RK = (long long)R * k;
+    if (RK >= 65535) return 1;                                     // slots are u16, 0xFFFF = none
+    GatherBwdPullParams p;
+    p.g_cube = g_cube; p.g_cabins = g_cabins; p.idx = idx; p.cab_arg = cab_arg; p.grad_x = grad_x;
+    p.rows = (long long)B * C;
+    p.C = C; p.N = N; p.R = R; p.k = k; p.cab = g_cabins ? cab : 1;
+    p.bulk_in = ((RK & 3) == 0) && (((uintptr_t)g_cube & 15) == 0);
+    p.vec_out = ((N & 3) == 0) && (((uintptr_t)grad_x & 15) == 0);
+    const size_t budget = (size_t)max_optin_smem();
+    const size_t fixed = 128 + (((((size_t)N + 3) & ~(size_t)3) * 2 + 127) & ~(size_t)127) + (((size_t)RK * 2 + 127) & ~(size_t)127);
+    size_t target = 75 * 1024;                                     // three CTAs per SM
+    if (const char* e = getenv("SPK_PULL_SMEM_KB")) target = (size_t)atoi(e) * 1024;
+    const int wins = R * p.cab;
+    // the window-max gradient rides along as bulk copies when every group's byte ranges are 16-byte multiples
+    p.cab_bulk = g_cabins != nullptr && (wins % 8) == 0 && (((uintptr_t)g_cabins & 15) == 0) && (((uintptr_t)cab_arg & 15) == 0);
+    if (getenv("SPK_PULL_NOCABBULK")) p.cab_bulk = 0;
+    // T rows per group: as many as keep three CTAs per SM; tables / tiles too large for that: up to two
+    // rows in one wide CTA per SM
+    int T = 8;
+    if (const char* e = getenv("SPK_PULL_T")) T = atoi(e);
+    else {
+        while (T > 1 && fixed + 2 * pull_slot_bytes(T, (int)RK, wins, p.cab_bulk) > target) T >>= 1;
+        if (T == 1 && fixed + 2 * pull_slot_bytes(1, (int)RK, wins, p.cab_bulk) > target &&
+            fixed + 2 * pull_slot_bytes(2, (int)RK, wins, p.cab_bulk) <= budget) T = 2;
+    }
+    T = std::max(1, std::min(8, T));
+    while (T > 1 && T / 2 >= C) T >>= 1;
+    const size_t tile = pull_slot_bytes(T, (int)RK, wins, p.cab_bulk);
+    if (fixed + 2 * tile > budget) return 1;
+    int ng = 2;
+    if (const char* e = getenv("SPK_PULL_NG")) ng = atoi(e);
+    ng = std::max(2, std::min(8, ng));
+    while (ng > 2 && fixed + (size_t)ng * tile > std::max(target, fixed + 2 * tile)) --ng;
+    p.ng = ng;
+    p.dbg = 0;
+    if (const char* e = getenv("SPK_PULL_DBG")) p.dbg = atoi(e);
+    const size_t smem = fixed + (size_t)ng * tile;
+    // CTA width: narrow CTAs (128 threads) put more independent CTAs on an SM, so one CTA's table build /
+    // tile wait / fold overlaps another's stores (measured at config A: 14.0 us vs 18.6 us with 256);
+    // with at most two resident CTAs (large tables / tiles) 512 threads keep enough warps per SM
+    int threads = 128;
+    if (T < 8 && (228 * 1024) / (smem + 1024) <= 2) threads = 512;
+    if (const char* e = getenv("SPK_PULL_THREADS")) threads = atoi(e);
+    if (T == 8 && threads > 256) threads = 256;
+#define SPK_PULL_CASE(TT)                                                            \
+    case TT:                                                                         \
+        if (threads >= 512 && TT < 8) return launch_pull<TT, (TT < 8 ? 512 : 256)>(p, smem, stream); \
+        if (threads >= 256) return launch_pull<TT, 256>(p, smem, stream);            \
+        if (threads >= 128) return launch_pull<TT, 128>(p, smem, stream);            \
+        return launch_pull<TT, 64>(p, smem, stream);
+    switch (T) {
+        SPK_PULL_CASE(8)
+        SPK_PULL_CASE(4)
+        SPK_PULL_CASE(2)
+        default:
+        SPK_PULL_CASE(1)
+    }
+#undef SPK_PULL_CASE
+}
+
 extern "C" int sp_gather_bwd_f32(const float* g_cube, const float* g_cabins, const int32_t* idx,
                                  const uint16_t* cab_arg, int B, int C, int N, int R, int k,
                                  int cab, float* grad_x, void* stream) {
@@ -508,6 +827,13 @@ extern "C" int sp_gather_bwd_f32(const float* g_cube, const float* g_cabins, con
     }
     if (N > 65536) return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: N=%d > 65536", N);
     if ((long long)B * C >= (1LL << 31)) return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: B*C >= 2^31");
+    // default: pull (inverse table + register accumulation, direct stores); SPK_BWD=push selects the
+    // shared-memory scatter kernel, which also serves sizes the pull kernel does not take
+    const char* mode = getenv("SPK_BWD");
+    if (!(mode && mode[0] == 'p' && mode[1] == 'u' && mode[2] == 's')) {
+        const int rc = gather_bwd_pull(g_cube, g_cabins, idx, cab_arg, B, C, N, R, k, cab, grad_x, (cudaStream_t)stream);
+        if (rc != 1) return rc;
+    }
     return gather_bwd_push(g_cube, g_cabins, idx, cab_arg, B, C, N, R, k, cab, grad_x, (cudaStream_t)stream);
 }
 

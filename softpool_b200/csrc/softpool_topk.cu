@@ -68,6 +68,9 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     uint32_t* sk = reinterpret_cast<uint32_t*>(sel + K2);                  // E*256 keys, [e][t]
     int* hist = reinterpret_cast<int*>(sk + (size_t)E * TOPK_THREADS);     // 3 x 8 warps x 16 bins
     __shared__ int warp_tot[TOPK_THREADS / 32];
+    __shared__ uint32_t cand_list[32];
+    __shared__ int cand_cnt;
+    __shared__ uint32_t v_final;
     const int tid = threadIdx.x;
     const int row = blockIdx.x;
     const int b = row / R, r = row - b * R;
@@ -116,6 +119,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     }
     for (int i = tid; i < K2; i += TOPK_THREADS) sel[i] = 0ull;
     for (int i = tid; i < 3 * 8 * 16; i += TOPK_THREADS) hist[i] = 0;
+    if (tid == 0) cand_cnt = 0;
 
     // ---- argmax over the R rows for this CTA's slice of n (softpool.py:95) --------------------------
     if (id_activa != nullptr) {
@@ -142,6 +146,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     // atomics), one barrier per round; every warp then reduces the 8 histograms itself.
     // (8-bit digits / 256-bin histograms: measured slower, 17.4 vs 12.5 us at N=2048.)
     uint32_t V = 0;
+    int fin_sh = -1;                                     // >= 0: the select stopped early with bits [31:fin_sh] decided
     int want = k;                                        // rank still to be located inside the prefix bucket
     const int lane = tid & 31, warp = tid >> 5;
     for (int round = 0; round < 8; ++round) {
@@ -172,9 +177,37 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         const int above = __shfl_sync(0xFFFFFFFFu, S - c, dsel);                   // candidates with a larger digit
         want -= above;
         V |= (uint32_t)dsel << sh;
+        // few candidates left in the chosen bucket: one warp ranks them directly (below) instead of
+        // spending the remaining rounds (a barrier and a reduction each) on a handful of keys.
+        // c, S, dsel are identical in every warp, so the branch is uniform.
+        if (round < 7 && __shfl_sync(0xFFFFFFFFu, c, dsel) <= 32) { fin_sh = sh; break; }
         // recycle the histogram used two rounds from now (everybody is past the barrier of the previous round)
         int* Hz = hist + ((round + 2) % 3) * (8 * 16);
         if (tid < 8 * 16) Hz[tid] = 0;
+    }
+
+    if (fin_sh >= 0) {
+        // the bucket's <= 32 keys -> shared list; warp 0 finds the one with exactly want-1 keys ahead of it
+        const uint32_t pre = V >> fin_sh;
+#pragma unroll 4
+        for (int e = 0; e < E; ++e) {
+            const uint32_t key = sk[e * TOPK_THREADS + tid];
+            if ((key >> fin_sh) == pre) cand_list[atomicAdd(&cand_cnt, 1)] = key;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int nc = cand_cnt;
+            const uint32_t key = lane < nc ? cand_list[lane] : 0u;
+            int ahead = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t o = __shfl_sync(0xFFFFFFFFu, key, j);
+                ahead += (j < nc) && (o > key || (o == key && j < lane));
+            }
+            if (lane < nc && ahead == want - 1) v_final = key;
+        }
+        __syncthreads();
+        V = v_final;
     }
 
     TQ(2);
@@ -190,9 +223,8 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     const int ge_before = block_exclusive_scan((my_gt << 16) | my_eq, warp_tot, tid, total_ge);
     const int eq_before = ge_before & 0xFFFF, total_gt = total_ge >> 16;
     const int need = k - total_gt;                       // >= 1 ties to take, lowest indices first
-    const int my_eq_taken = max(0, min(my_eq, need - eq_before));
-    int total_sel;
-    int pos = block_exclusive_scan(my_gt + my_eq_taken, warp_tot, tid, total_sel);
+    // the ties taken are the first `need` in index order, so the ones before this thread are min(eq_before, need)
+    int pos = (ge_before >> 16) + min(eq_before, need);
     int eq_rank = eq_before;
     for (int e = 0; e < E; ++e) {
         const uint32_t key = sk[e * TOPK_THREADS + tid];
