@@ -101,6 +101,8 @@ struct PrepParams {
     unsigned char* A1; unsigned char* B1; unsigned char* A2; unsigned char* B2;   // per sample n_pad*32 / m_pad*32 bytes
     float4* T1; float4* T2;          // raw coordinates (x,y,z,0), padded per sample to n_pad / m_pad rows
     ChamferMeta* meta;
+    unsigned long long* packed1; unsigned long long* packed2;   // split jobs only: (dist bits << 32 | idx) minima, B*n / B*m
+    int* counters; int n_counters;   // split jobs only: arrivals per (sample, direction, query tile)
 };
 
 __global__ void __launch_bounds__(256)
@@ -192,7 +194,11 @@ chamfer_prep_kernel(const PrepParams p) {
         }
         write_rows(first ? A1 : A2, first ? B1 : B2, r, real, ux, uy, uz);
         (first ? p.T1 + (size_t)b * p.n_pad : p.T2 + (size_t)b * p.m_pad)[r] = raw;
+        if (real && p.packed1 != nullptr)
+            (first ? p.packed1 + (size_t)b * p.n : p.packed2 + (size_t)b * p.m)[r] = ~0ull;
     }
+    if (p.counters != nullptr && blockIdx.x == 0)
+        for (int i = tid; i < p.n_counters; i += 256) p.counters[(size_t)b * p.n_counters + i] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -282,17 +288,20 @@ struct TcParams {
     float* dist1; float* dist2; int32_t* idx1; int32_t* idx2;
     int B, n, m, n_pad, m_pad;
     int tiles1, tiles2;      // query tiles per sample in direction 0 / 1
+    int S1, S2;              // target-range splits per query tile in direction 0 / 1 (1 = whole range in one job)
+    unsigned long long* packed1; unsigned long long* packed2; int* counters;    // merge of split jobs
 };
 
 struct __align__(128) TcSmem {
-    unsigned char a_tile[TC_TILE_BYTES];
+    unsigned char a_tile[2][TC_TILE_BYTES];                    // double-buffered: the next job's queries arrive early
     unsigned char b_tile[TC_STAGES][TC_TILE_BYTES];
     float4 t4[2][TC_SB_TARGETS];                               // raw target coordinates, per super-block
-    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full, a_empty, tmem_full[TC_NBUF], tmem_empty[TC_NBUF], t4_full[2], t4_empty[2];
+    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full[2], a_empty[2], tmem_full[TC_NBUF], tmem_empty[TC_NBUF], t4_full[2], t4_empty[2];
     uint32_t tmem_base;
     float rowmin[2][2][TC_TILE];          // [super-block parity][column half][row]
     float best_d[TC_TILE]; int best_i[TC_TILE];
     int dbg[2];
+    int last;                             // split jobs: this CTA finished the query tile's last sub-job
 };
 
 __device__ __forceinline__ float min16(const float* v) {
@@ -307,12 +316,12 @@ chamfer_tc_kernel(const TcParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int jobs_per_sample = p.tiles1 + p.tiles2;
+    const int jobs_per_sample = p.tiles1 * p.S1 + p.tiles2 * p.S2;
     const int total_jobs = jobs_per_sample * p.B;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-        mbar_init(&S.a_full, 1); mbar_init(&S.a_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1); }
         for (int i = 0; i < TC_NBUF; ++i) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], 8); }
         for (int i = 0; i < 2; ++i) { mbar_init(&S.t4_full[i], 1); mbar_init(&S.t4_empty[i], 8); }
         fence_mbar_init();
@@ -328,6 +337,14 @@ chamfer_tc_kernel(const TcParams p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+#ifdef SPK_TIMING
+    const long long tk0 = clock64();
+    __shared__ long long tlog_t[96]; __shared__ int tlog_a[96]; __shared__ int tlog_b[96]; __shared__ const char* tlog_s[96]; __shared__ int tlog_n;
+    if (tid == 0) tlog_n = 0;
+#define TCLOG(tag, a, b) do { if (blockIdx.x == 0 && warp == 2 && lane == 0 && tlog_n < 96) { tlog_t[tlog_n] = clock64() - tk0; tlog_s[tlog_n] = tag; tlog_a[tlog_n] = (int)(a); tlog_b[tlog_n] = (int)(b); ++tlog_n; } } while (0)
+#else
+#define TCLOG(tag, a, b)
+#endif
     const uint32_t tmem_base = S.tmem_base;
     pdl_wait();                  // operands / metadata come from chamfer_prep_kernel
 
@@ -335,24 +352,33 @@ chamfer_tc_kernel(const TcParams p) {
     uint32_t ring_it = 0, acc_it = 0, sb_it = 0, job_it = 0;
 
     for (int job_id = blockIdx.x; job_id < total_jobs; job_id += gridDim.x, ++job_it) {
-        const int b = job_id / jobs_per_sample;
+        const int b = (int)((unsigned)job_id / (unsigned)jobs_per_sample);
         int job = job_id - b * jobs_per_sample;
-        const int dir = job < p.tiles1 ? 0 : 1;
-        if (dir) job -= p.tiles1;
+        const int dir = job < p.tiles1 * p.S1 ? 0 : 1;
+        if (dir) job -= p.tiles1 * p.S1;
+        const int NS = dir ? p.S2 : p.S1;
         const int nq = dir ? p.m : p.n, nt = dir ? p.n : p.m;
         const int nq_pad = dir ? p.m_pad : p.n_pad, nt_pad = dir ? p.n_pad : p.m_pad;
-        const int T = nt_pad / TC_TILE;                        // target tiles
-        const int n_sb = T / TC_SB_TILES;                      // rows are padded to whole super-blocks
+        const int n_sb_all = nt_pad / TC_SB_TARGETS;           // rows are padded to whole super-blocks
+        int sb0 = 0, sb1 = n_sb_all;
+        if (NS > 1) {                                          // (the common unsplit case pays no divisions)
+            const int split = (int)((unsigned)job % (unsigned)NS);      // sub-jobs of one query tile are neighbours:
+            job = (int)((unsigned)job / (unsigned)NS);                  // they run together and share the A tile in L2
+            sb0 = split * n_sb_all / NS; sb1 = (split + 1) * n_sb_all / NS;
+        }
+        const int n_sb = sb1 - sb0;                            // super-blocks of this (sub-)job: [sb0, sb1)
+        const int T = n_sb * TC_SB_TILES;                      // target tiles of this (sub-)job
 
         if (warp == 0) {
             // ===== TMA producer =====
             if (lane == 0) {
                 const unsigned char* Aop = (dir ? p.A2 : p.A1) + ((size_t)b * nq_pad + (size_t)job * TC_TILE) * 32;
-                const unsigned char* Bop = (dir ? p.B1 : p.B2) + (size_t)b * nt_pad * 32;
-                const float4* T4 = (dir ? p.T1 : p.T2) + (size_t)b * nt_pad;
-                mbar_wait(&S.a_empty, (uint32_t)((job_it & 1) ^ 1));       // previous job's MMAs have read A
-                mbar_expect_tx(&S.a_full, TC_TILE_BYTES);
-                bulk_g2s(S.a_tile, Aop, TC_TILE_BYTES, &S.a_full);
+                const unsigned char* Bop = (dir ? p.B1 : p.B2) + ((size_t)b * nt_pad + (size_t)sb0 * TC_SB_TARGETS) * 32;
+                const float4* T4 = (dir ? p.T1 : p.T2) + (size_t)b * nt_pad + (size_t)sb0 * TC_SB_TARGETS;
+                const uint32_t ab = job_it & 1;
+                mbar_wait(&S.a_empty[ab], (uint32_t)(((job_it >> 1) & 1) ^ 1));   // the job two back has read this buffer
+                mbar_expect_tx(&S.a_full[ab], TC_TILE_BYTES);
+                bulk_g2s(S.a_tile[ab], Aop, TC_TILE_BYTES, &S.a_full[ab]);
                 for (int sb = 0; sb < n_sb; ++sb) {
                     const uint32_t sbi = sb_it + sb, pb = sbi & 1;
                     constexpr int tiles = TC_SB_TILES;
@@ -370,8 +396,9 @@ chamfer_tc_kernel(const TcParams p) {
         } else if (warp == 1) {
             // ===== MMA issuer =====
             if (lane == 0) {
-                mbar_wait(&S.a_full, (uint32_t)(job_it & 1));
-                const uint64_t a_desc = umma_smem_desc(S.a_tile);
+                const uint32_t ab = job_it & 1;
+                mbar_wait(&S.a_full[ab], (uint32_t)((job_it >> 1) & 1));
+                const uint64_t a_desc = umma_smem_desc(S.a_tile[ab]);
                 for (int t = 0; t < T; ++t) {
                     const uint32_t it = ring_it + t, s = it % TC_STAGES;
                     mbar_wait(&S.full[s], (uint32_t)((it / TC_STAGES) & 1));
@@ -385,7 +412,7 @@ chamfer_tc_kernel(const TcParams p) {
                     }
                     umma_commit(&S.empty[s]);            // smem slot free once both MMAs have read it
                 }
-                umma_commit(&S.a_empty);                 // A tile may be replaced
+                umma_commit(&S.a_empty[ab]);             // this A buffer may be replaced
             }
         } else {
             // ===== epilogue: 8 warps; warp%4 picks the TMEM lane quarter, (warp-2)/4 the column half =====
@@ -401,10 +428,12 @@ chamfer_tc_kernel(const TcParams p) {
             // reference: the first target initialises the running best (`k==0 || d<best`, chamfer.cu:36).
             // The loads are issued here, the distance is formed at the first filter: their latency hides
             // behind the first super-block's min pass.
-            const float t0x = __ldg(Tx), t0y = __ldg(Tx + 1), t0z = __ldg(Tx + 2);
+            const int t_first = sb0 * TC_SB_TARGETS;                // first target of this (sub-)job: always a real point
+            const float t0x = __ldg(Tx + 3 * (size_t)t_first), t0y = __ldg(Tx + 3 * (size_t)t_first + 1), t0z = __ldg(Tx + 3 * (size_t)t_first + 2);
             float best_d = 0.f;
-            int best_i = 0;
+            int best_i = t_first;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * (TC_N / 2);
+            TCLOG("job start", job_id, n_sb);
 
             for (int sb = 0; sb < n_sb; ++sb) {
                 // per thread: TC_N/2 columns of every accumulator = TC_N/32 chunks of 16 targets
@@ -415,6 +444,7 @@ chamfer_tc_kernel(const TcParams p) {
                 for (int a = 0; a < ACC_PER_SB; ++a) {
                     const uint32_t ai = acc_it + (uint32_t)(sb * ACC_PER_SB + a), buf = ai % TC_NBUF;
                     mbar_wait(&S.tmem_full[buf], (ai / TC_NBUF) & 1);
+                    if (a == 0) TCLOG(" sb first acc ready", sb, 0);
                     tc_fence_after();
                     const uint32_t ta = lane_addr + buf * TC_N;
                     float va[16], vb[16];
@@ -432,6 +462,7 @@ chamfer_tc_kernel(const TcParams p) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.tmem_empty[buf]);      // accumulator buffer may be overwritten
                 }
+                TCLOG(" sb min pass done", sb, 0);
                 // ---- filter: chunks within tau of the row minimum (or of the exact best so far) ----
                 constexpr int NCM = CPA * ACC_PER_SB;                       // 32
                 float rmin = min3(cm[0], cm[1], cm[2]);
@@ -455,7 +486,8 @@ chamfer_tc_kernel(const TcParams p) {
                 const uint32_t sbi = sb_it + sb, pb = sbi & 1;
                 mbar_wait(&S.t4_full[pb], (uint32_t)((sbi >> 1) & 1));
                 const float4* tsm = S.t4[pb];
-                const int sb_base = sb * TC_SB_TARGETS;
+                TCLOG(" sb filter done, t4 ready", sb, __popc(mask));
+                const int sb_base = (sb0 + sb) * TC_SB_TARGETS;
                 while (mask) {
                     const int i = __ffs(mask) - 1;
                     mask &= mask - 1;
@@ -482,6 +514,7 @@ chamfer_tc_kernel(const TcParams p) {
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.t4_empty[pb]);
+                TCLOG(" sb exact done", sb, 0);
             }
             // ---- merge the two column halves of each row, first minimum wins ----
             if (h == 1) { S.best_d[row] = best_d; S.best_i[row] = best_i; }
@@ -489,15 +522,44 @@ chamfer_tc_kernel(const TcParams p) {
             if (h == 0 && live) {
                 const float d2 = S.best_d[row]; const int i2 = S.best_i[row];
                 if (d2 < best_d || (d2 == best_d && i2 < best_i)) { best_d = d2; best_i = i2; }
-                ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = best_d;
-                ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = best_i;
+                if (NS == 1) {
+                    ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = best_d;
+                    ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = best_i;
+                } else {
+                    // distances are >= +0: their bit patterns order like the values, the index breaks ties
+                    // downwards -> the 64-bit minimum over the sub-jobs IS the first minimum
+                    atomicMin((dir ? p.packed2 : p.packed1) + (size_t)b * nq + gq,
+                              ((unsigned long long)__float_as_uint(best_d) << 32) | (unsigned)best_i);
+                }
+            }
+            if (NS > 1) {
+                // the sub-job that arrives last at the query tile's counter unpacks the merged minima.
+                // Ordering: the CTA barrier orders the threads' atomics before the elected thread's
+                // acq_rel increment (release, cumulative); the last arriver's increment acquires every
+                // earlier sub-job's minima, the second barrier hands that to its other threads.
+                epi_bar();
+                if (warp == 2 && lane == 0) {
+                    int* cnt = p.counters + (size_t)b * (p.tiles1 + p.tiles2) + (dir ? p.tiles1 : 0) + job;
+                    int old;
+                    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(cnt) : "memory");
+                    S.last = (old == NS - 1);
+                }
+                epi_bar();
+                if (S.last && h == 0 && live) {
+                    unsigned long long v;
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"((dir ? p.packed2 : p.packed1) + (size_t)b * nq + gq) : "memory");
+                    ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = __uint_as_float((unsigned)(v >> 32));
+                    ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = (int)(unsigned)v;
+                }
             }
         }
+        if (warp >= 2) TCLOG("job end", job_id, 0);
         ring_it += (uint32_t)T; acc_it += (uint32_t)(TC_TILE / TC_N) * (uint32_t)T; sb_it += (uint32_t)n_sb;
     }
 
 #ifdef SPK_TIMING
     __syncthreads();
+    if (tid == 0 && blockIdx.x == 0) for (int i = 0; i < tlog_n; ++i) printf("  t=%7lld %s %d %d\n", tlog_t[i], tlog_s[i], tlog_a[i], tlog_b[i]);
     if (tid == 0 && blockIdx.x < 2) printf("tc cta %d: chunks evaluated %d over %d (row, half, super-block) filters = %.3f each\n", blockIdx.x, S.dbg[0], S.dbg[1], (float)S.dbg[0] / (float)max(S.dbg[1], 1));
 #endif
     tc_fence_before();
@@ -513,8 +575,10 @@ static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
 size_t chamfer_tc_workspace_bytes(int B, int n, int m) {
     const size_t n_pad = round_up(n, TC_SB_TARGETS), m_pad = round_up(m, TC_SB_TARGETS);
+    const size_t tiles = (size_t)(n + TC_TILE - 1) / TC_TILE + (size_t)(m + TC_TILE - 1) / TC_TILE;
     return 2 * (size_t)B * (n_pad + m_pad) * 32 + (size_t)B * (n_pad + m_pad) * 16 +
-           (((size_t)B * sizeof(ChamferMeta) + 255) & ~(size_t)255) + 256;
+           (((size_t)B * sizeof(ChamferMeta) + 255) & ~(size_t)255) + 256 +
+           (size_t)B * ((size_t)n + m) * 8 + ((((size_t)B * tiles * 4) + 255) & ~(size_t)255) + 256;    // split-job merge
 }
 
 int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
@@ -533,6 +597,35 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
     pp.A1 = ops; pp.B1 = pp.A1 + (size_t)B * n_pad * 32;
     pp.A2 = pp.B1 + (size_t)B * n_pad * 32; pp.B2 = pp.A2 + (size_t)B * m_pad * 32;
     pp.T1 = reinterpret_cast<float4*>(pp.B2 + (size_t)B * m_pad * 32); pp.T2 = pp.T1 + (size_t)B * n_pad;
+    // Fewer jobs than persistent CTAs (small batches: B=1 validation clouds): the target range of every
+    // query tile is split into sub-jobs that merge through a 64-bit atomicMin; the last one to arrive
+    // unpacks.  A sub-job costs ~1.5 us of merge on top of ~3 us per super-block (measured), so splitting
+    // only pays when the grid is underfilled; the split minimising the makespan estimate wins.
+    // (Splitting to even out the tail of config A -- 3.46 jobs per CTA -- was measured SLOWER: 45.8 vs 33.4 us.)
+    const int tiles1 = (n + TC_TILE - 1) / TC_TILE, tiles2 = (m + TC_TILE - 1) / TC_TILE;
+    const long long ctas = 2LL * sm_count();
+    const long long jobs1 = (long long)(tiles1 + tiles2) * B;
+    int split = 1;
+    if (jobs1 < ctas) {
+        const double sb_avg = 0.5 * (n_pad + m_pad) / TC_SB_TARGETS;          // super-blocks per unsplit job
+        double best = 1e30;
+        for (int c = 1; c <= 8; c *= 2) {
+            const double waves = (double)((jobs1 * c + ctas - 1) / ctas);
+            const double cost = waves * (3.0 * sb_avg / c + (c > 1 ? 1.5 : 0.0));
+            if (cost < best - 1e-9) { best = cost; split = c; }
+        }
+    }
+    if (const char* e = getenv("SPK_TC_SPLIT")) split = std::max(1, std::min(64, atoi(e)));
+    const int S1 = std::max(1, std::min(split, m_pad / TC_SB_TARGETS));    // direction 0 scans xyz2
+    const int S2 = std::max(1, std::min(split, n_pad / TC_SB_TARGETS));
+    pp.packed1 = nullptr; pp.packed2 = nullptr; pp.counters = nullptr; pp.n_counters = tiles1 + tiles2;
+    if (S1 > 1 || S2 > 1) {
+        unsigned char* q = reinterpret_cast<unsigned char*>(pp.T2 + (size_t)B * m_pad);
+        q = reinterpret_cast<unsigned char*>(((uintptr_t)q + 255) & ~(uintptr_t)255);
+        pp.packed1 = reinterpret_cast<unsigned long long*>(q);
+        pp.packed2 = pp.packed1 + (size_t)B * n;
+        pp.counters = reinterpret_cast<int*>(pp.packed2 + (size_t)B * m);
+    }
     const int slices = std::max(1, std::min(16, (n_pad + m_pad) / 512));
     SPK_CUDA(launch_k(chamfer_prep_kernel, dim3(slices, B), dim3(256), 0, st, pp));
 
@@ -540,11 +633,12 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
     tp.xyz1 = xyz1; tp.xyz2 = xyz2; tp.A1 = pp.A1; tp.B1 = pp.B1; tp.A2 = pp.A2; tp.B2 = pp.B2; tp.T1 = pp.T1; tp.T2 = pp.T2; tp.meta = pp.meta; tp.B = B;
     tp.dist1 = dist1; tp.dist2 = dist2; tp.idx1 = idx1; tp.idx2 = idx2;
     tp.n = n; tp.m = m; tp.n_pad = n_pad; tp.m_pad = m_pad;
-    tp.tiles1 = (n + TC_TILE - 1) / TC_TILE; tp.tiles2 = (m + TC_TILE - 1) / TC_TILE;
+    tp.tiles1 = tiles1; tp.tiles2 = tiles2; tp.S1 = S1; tp.S2 = S2;
+    tp.packed1 = pp.packed1; tp.packed2 = pp.packed2; tp.counters = pp.counters;
     // request enough shared memory that at most 2 CTAs share an SM (each owns 256 of the 512 TMEM columns)
     const size_t smem = std::max(sizeof(TcSmem) + 128, (size_t)80 * 1024);
     SPK_CUDA(cudaFuncSetAttribute(chamfer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long jobs = (long long)(tp.tiles1 + tp.tiles2) * B;
+    const long long jobs = ((long long)tp.tiles1 * S1 + (long long)tp.tiles2 * S2) * B;
     const int grid = (int)std::min<long long>(jobs, 2LL * sm_count());         // persistent: 2 CTAs per SM
     SPK_CUDA(launch_k(chamfer_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tp));
     return SPK_OK;
