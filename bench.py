@@ -145,7 +145,7 @@ class BufferSet:
 
 
 KERNELS = ["sp_topk_f32", "sp_gather_fwd_f32", "sp_gather_bwd_f32", "chamfer_fwd_f32", "chamfer_loss_f32", "chamfer_bwd_f32"]
-LAUNCHES_PER_STEP = 8     # chamfer_fwd_f32 = prep + tensor kernel, chamfer_bwd_f32 = direct + scatter
+LAUNCHES_PER_STEP = 7     # chamfer_fwd_f32 = prep + tensor kernel; every other call is one kernel
 
 
 class Step:
@@ -227,6 +227,44 @@ def run_b200(args, w, rank, local_rank, world):
     points_per_step = spd.sum_over_ranks(B * N, dev)
     value = points_per_step / (ms_per_step * 1e-3) / 1e6
 
+    # ---- informational: the SoftPool chain and the Chamfer chain are independent in this metric; captured as
+    # two branches of one CUDA graph they overlap (HBM-bound gather kernels next to the ALU-bound Chamfer
+    # kernel).  Reported beside `value`, never instead of it.
+    overlap = None
+    try:
+        side = torch.cuda.Stream(device=dev)
+        graphs2 = []
+        with torch.cuda.stream(stream):
+            for s in sets:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, stream=stream):
+                    fork, join = torch.cuda.Event(), torch.cuda.Event()
+                    fork.record(stream)
+                    side.wait_event(fork)
+                    cl = step.calls(s)
+                    with torch.cuda.stream(side):
+                        for _, f in cl[3:]:
+                            f()
+                        join.record(side)
+                    for _, f in cl[:3]:
+                        f()
+                    stream.wait_event(join)
+                graphs2.append(g2)
+            for i in range(args.warmup):
+                graphs2[i % nsets].replay()
+            stream.synchronize()
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            o0.record(stream)
+            for i in range(args.steps):
+                graphs2[i % nsets].replay()
+            o1.record(stream)
+            stream.synchronize()
+        o_ms = spd.max_over_ranks(o0.elapsed_time(o1), dev) / args.steps
+        overlap = {"ms_per_step": o_ms, "value": points_per_step / (o_ms * 1e-3) / 1e6, "unit": UNIT,
+                   "how": "same step, SoftPool chain and Chamfer chain as two branches of one CUDA graph"}
+    except Exception as e:                      # informational leg: never fail the bench line
+        overlap = {"error": repr(e)[:200]}
+
     # ---- per-kernel device time: every C-ABI call captured alone in a CUDA graph (30 launches rotating
     # over the buffer sets, so its inputs are not L2-resident), CUDA events around 5 replays on `stream`
     kern_us = {}
@@ -285,32 +323,47 @@ def run_b200(args, w, rank, local_rank, world):
             "roofline": dominant, "roofline_softpool": roof_sp, "roofline_chamfer": roof_ch,
             "kernel_us": kern_us, "softpool_fwd_bwd_us": sp_us, "chamfer_fwd_bwd_us": ch_us,
             "kernel_timing": "per C-ABI call: CUDA events around 5 replays of a CUDA graph holding %d launches that rotate over the %d buffer sets" % (reps, nsets),
+            "chains_overlapped": overlap,
             "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "clocks": clocks,
         }
     return out
 
 
 def run_e2e(args, w, dev, stream, spd):
+    """Same step through the public Python API with HOST (pinned) inputs.  Every step copies all of its
+    inputs host->device and its results device->host inside the timed region.  The copies run on a copy
+    stream into one of two device input sets, so step i+1's H2D overlaps step i's kernels (what a user's
+    prefetching data loader does); events order copy -> compute -> reuse of the set."""
     import torch
     import softpool_b200 as spb
     from softpool_b200 import ops
     B, C, N, R, k, cab = (w[x] for x in "B C N R k cab".split())
     g = torch.Generator().manual_seed(7)
     pin = lambda t: t.pin_memory()
-    hx, hk = pin(torch.randn(B, C, N, generator=g)), pin(torch.randn(B, R, N, generator=g))
-    hgc, hgb = pin(torch.randn(B, C, R, k, generator=g)), pin(torch.randn(B, C, R, cab, generator=g))
-    h1, h2 = pin(torch.rand(B, N, 3, generator=g) - 0.5), pin(torch.rand(B, N, 3, generator=g) - 0.5)
+    host = [pin(torch.randn(B, C, N, generator=g)), pin(torch.randn(B, R, N, generator=g)),
+            pin(torch.randn(B, C, R, k, generator=g)), pin(torch.randn(B, C, R, cab, generator=g)),
+            pin(torch.rand(B, N, 3, generator=g) - 0.5), pin(torch.rand(B, N, 3, generator=g) - 0.5)]
     out_cab = pin(torch.empty(B, C, R, cab)); out_loss = pin(torch.empty(B)); out_g1 = pin(torch.empty(B, N, 3))
     cd = spb.chamferDist()
-    h2d = sum(t.numel() * t.element_size() for t in (hx, hk, hgc, hgb, h1, h2))
+    h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = sum(t.numel() * t.element_size() for t in (out_cab, out_loss, out_g1))
+    copy_stream = torch.cuda.Stream(device=dev)
+    dsets = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]       # set j holds fresh inputs
+    free = [torch.cuda.Event() for _ in range(2)]        # the step that used set j is done with it
 
-    def one():
-        x = hx.to(dev, non_blocking=True).requires_grad_(True)
-        keys = hk.to(dev, non_blocking=True)
-        gc, gb = hgc.to(dev, non_blocking=True), hgb.to(dev, non_blocking=True)
-        a = h1.to(dev, non_blocking=True).requires_grad_(True)
-        b = h2.to(dev, non_blocking=True)
+    def upload(j):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[j])
+            for d, h in zip(dsets[j], host):
+                d.copy_(h, non_blocking=True)
+            ready[j].record(copy_stream)
+
+    def compute(j):
+        stream.wait_event(ready[j])
+        dx, keys, gc, gb, a, b = dsets[j]
+        x = dx.detach().requires_grad_(True)
+        a = a.detach().requires_grad_(True)
         idx, sp_idx, id_activa = ops.softpool_topk(keys, k)
         sp_cube, cabins = ops.softpool_gather(x, idx, cab)
         torch.autograd.backward([sp_cube, cabins], [gc, gb])
@@ -320,24 +373,36 @@ def run_e2e(args, w, dev, stream, spd):
         out_cab.copy_(cabins.detach(), non_blocking=True)
         out_loss.copy_(loss.detach(), non_blocking=True)
         out_g1.copy_(a.grad, non_blocking=True)
+        free[j].record(stream)
+
+    def run(nsteps):
+        upload(0)
+        for i in range(nsteps):
+            if i + 1 < nsteps:
+                upload((i + 1) & 1)
+            compute(i & 1)
 
     steps = max(5, min(args.steps, 30))
     with torch.cuda.stream(stream):
-        for _ in range(3):
-            one()
-        stream.synchronize()
+        for j in range(2):
+            free[j].record(stream)
+        run(3)
+        stream.synchronize(); copy_stream.synchronize()
         spd.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps):
-            one()
-        e1.record(stream)
-        stream.synchronize()
+        copy_stream.wait_event(e0)                       # no copy of the timed steps starts before the clock does
+        for j in range(2):
+            free[j].record(stream)
+        run(steps)
+        e1.record(stream)                                # after the last step's kernels and D2H copies
+        stream.synchronize(); copy_stream.synchronize()
     ms = spd.max_over_ranks(e0.elapsed_time(e1), dev) / steps
     pts = spd.sum_over_ranks(B * N, dev)
     return {"value": pts / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "api": "ops.softpool_topk + ops.softpool_gather (autograd) + chamferDist (autograd), pinned host tensors"}
+            "api": "ops.softpool_topk + ops.softpool_gather (autograd) + chamferDist (autograd); pinned host tensors, "
+                   "H2D of step i+1 on a copy stream under step i's kernels (two device input sets)"}
 
 
 # ---------------------------------------------------------------------------------------------

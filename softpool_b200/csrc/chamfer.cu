@@ -123,6 +123,83 @@ __global__ void chamfer_bwd_scatter_kernel(const float* __restrict__ xyz1, const
     }
 }
 
+// Both passes in ONE launch: a thread-block cluster per sample.  Every thread keeps its points' terms in
+// registers, writes the direct terms (pass A), the cluster barrier (release/acquire at cluster scope)
+// orders those plain stores before the scatter atomics (pass B) of the whole sample -- every address a
+// sample's atomics touch was written by a CTA of the same cluster.  Halves the latency of the
+// two-kernel form (two launches + two dependent load chains) for these tiny arrays.
+constexpr int CHB_THREADS = 512;
+constexpr int CHB_PPT = 4;       // points per thread held in registers; more are recomputed in pass B
+
+__device__ __forceinline__ void chb_term(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                                         const float* __restrict__ g1, const float* __restrict__ g2,
+                                         const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2,
+                                         int b, int n, int m, int e, float v[3], long long& self, long long& other, bool& first) {
+    first = e < n;
+    const int q = first ? e : e - n;
+    const int nq = first ? n : m, nt = first ? m : n;
+    self = ((long long)b * nq + q) * 3;
+    const int j2 = __ldg((first ? idx1 : idx2) + (long long)b * nq + q);
+    other = ((long long)b * nt + j2) * 3;
+    const float* P = (first ? xyz1 : xyz2) + self;
+    const float* Qp = (first ? xyz2 : xyz1) + other;
+    const float g = __fmul_rn(__ldg((first ? g1 : g2) + (long long)b * nq + q), 2.0f);
+    v[0] = __fmul_rn(g, __fsub_rn(__ldg(P + 0), __ldg(Qp + 0)));
+    v[1] = __fmul_rn(g, __fsub_rn(__ldg(P + 1), __ldg(Qp + 1)));
+    v[2] = __fmul_rn(g, __fsub_rn(__ldg(P + 2), __ldg(Qp + 2)));
+}
+
+__global__ void __launch_bounds__(CHB_THREADS)
+chamfer_bwd_cluster_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                           const float* __restrict__ g1, const float* __restrict__ g2,
+                           const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2,
+                           int n, int m, float* __restrict__ grad1, float* __restrict__ grad2) {
+    pdl_trigger();
+    pdl_wait();
+    uint32_t rank, csize;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    const int b = blockIdx.x / csize;
+    const int total = n + m;
+    const int stride = (int)csize * CHB_THREADS;
+    const int e0 = (int)rank * CHB_THREADS + threadIdx.x;
+    float v[CHB_PPT][3]; long long other[CHB_PPT]; bool first[CHB_PPT];
+    // pass A (reference chamfer.cu:166-168): direct terms, plain stores, every element written
+#pragma unroll
+    for (int u = 0; u < CHB_PPT; ++u) {
+        const int e = e0 + u * stride;
+        if (e < total) {
+            long long self;
+            chb_term(xyz1, xyz2, g1, g2, idx1, idx2, b, n, m, e, v[u], self, other[u], first[u]);
+            float* G = (first[u] ? grad1 : grad2) + self;
+            G[0] = v[u][0]; G[1] = v[u][1]; G[2] = v[u][2];
+        }
+    }
+    for (int e = e0 + CHB_PPT * stride; e < total; e += stride) {
+        float w[3]; long long self, oth; bool f;
+        chb_term(xyz1, xyz2, g1, g2, idx1, idx2, b, n, m, e, w, self, oth, f);
+        float* G = (f ? grad1 : grad2) + self;
+        G[0] = w[0]; G[1] = w[1]; G[2] = w[2];
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // pass B (reference chamfer.cu:169-171): scatter onto the matched points of the other cloud
+#pragma unroll
+    for (int u = 0; u < CHB_PPT; ++u) {
+        const int e = e0 + u * stride;
+        if (e < total) {
+            float* G = (first[u] ? grad2 : grad1) + other[u];
+            atomicAdd(G + 0, -v[u][0]); atomicAdd(G + 1, -v[u][1]); atomicAdd(G + 2, -v[u][2]);
+        }
+    }
+    for (int e = e0 + CHB_PPT * stride; e < total; e += stride) {
+        float w[3]; long long self, oth; bool f;
+        chb_term(xyz1, xyz2, g1, g2, idx1, idx2, b, n, m, e, w, self, oth, f);
+        float* G = (f ? grad2 : grad1) + oth;
+        atomicAdd(G + 0, -w[0]); atomicAdd(G + 1, -w[1]); atomicAdd(G + 2, -w[2]);
+    }
+}
+
 // ---- loss epilogue: loss[b] = mean(dist1[b]) + mean(dist2[b]) --------------------------------------
 __global__ void __launch_bounds__(256)
 chamfer_loss_kernel(const float* __restrict__ dist1, const float* __restrict__ dist2, int n, int m,
@@ -199,6 +276,23 @@ extern "C" int chamfer_bwd_f32(const float* xyz1, const float* xyz2, const float
     if (!xyz1 || !xyz2 || !g1 || !g2 || !idx1 || !idx2 || !grad_xyz1 || !grad_xyz2)
         return fail(SPK_E_BADARG, "chamfer_bwd_f32: null pointer");
     const long long t1 = (long long)B * n, t2 = (long long)B * m;
+    const char* two = getenv("SPK_CH_BWD_TWO_KERNELS");
+    if (!(two && two[0] == '1') && (long long)n + m < (1LL << 30)) {
+        // one cluster per sample, sized so that a thread holds <= CHB_PPT points when 8 CTAs suffice
+        const long long per_cta = (long long)CHB_THREADS * CHB_PPT;
+        int cl = 1;
+        while (cl < 8 && (long long)cl * per_cta < (long long)n + m) cl <<= 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(B * cl)); cfg.blockDim = dim3(CHB_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        SPK_CUDA(cudaLaunchKernelEx(&cfg, chamfer_bwd_cluster_kernel, xyz1, xyz2, g1, g2, idx1, idx2, n, m, grad_xyz1, grad_xyz2));
+        return SPK_OK;
+    }
     const int grid = (int)std::min<long long>((t1 + t2 + 255) / 256, (long long)sm_count() * 8);
     SPK_CUDA(launch_k(chamfer_bwd_direct_kernel, dim3(grid), dim3(256), 0, st, xyz1, xyz2, g1, g2, idx1, idx2, n, m, grad_xyz1, grad_xyz2, t1, t2));
     SPK_CUDA(launch_k(chamfer_bwd_scatter_kernel, dim3(grid), dim3(256), 0, st, xyz1, xyz2, g1, g2, idx1, idx2, n, m, grad_xyz1, grad_xyz2, t1, t2));
