@@ -19,7 +19,6 @@
 
 namespace spk {
 
-constexpr int G_THREADS = 256;
 
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
@@ -38,6 +37,7 @@ __device__ __forceinline__ int tile_rows(long long g, long long g_hi, int T, int
     return (int)r;
 }
 // cooperative load of one sample's index list into shared memory as u16 (4 independent loads in flight)
+template <int G_THREADS>
 __device__ __forceinline__ void stage_idx_u16(const int32_t* __restrict__ src, uint16_t* dst, int n, int tid) {
     int i = tid;
     for (; i + 3 * G_THREADS < n; i += 4 * G_THREADS) {
@@ -65,6 +65,7 @@ struct GatherFwdParams {
     int q_shift;          // log2(R*k/4) when that is a power of two, else -1
 };
 
+template <int G_THREADS>
 __global__ void __launch_bounds__(G_THREADS)
 sp_gather_fwd_kernel(const GatherFwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -106,7 +107,7 @@ sp_gather_fwd_kernel(const GatherFwdParams p) {
         const int rows = tile_rows(g, g_hi, T, C);
         const int b = (int)((unsigned)g / (unsigned)C);
         if (b != cur_b) {                                // new sample: its index list (readers of the old one
-            stage_idx_u16(p.idx + (size_t)b * RK, idx_s, RK, tid);      // passed the barrier ending the last tile)
+            stage_idx_u16<G_THREADS>(p.idx + (size_t)b * RK, idx_s, RK, tid);   // passed the barrier ending the last tile)
             cur_b = b;
             __syncthreads();
         }
@@ -672,17 +673,27 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
                  (G == 1 || ((RK >> 2) % 32) == 0);
     p.g_shift = p.cab_fast ? ilog2_exact(G) : 0;
     p.q_shift = ilog2_exact((int)(RK >> 2));
-    // T rows per tile: two tiles of ~32 KB each -> 3 CTAs (24 warps) per SM
-    int T = (int)std::max<size_t>(1, std::min<size_t>(16, (32 * 1024) / row_bytes));
+    // tile size / CTA width: 256 threads with two ~32 KB tiles (3 CTAs per SM), or -- SPK_FWD_THREADS=128 --
+    // narrow CTAs with two ~16 KB tiles (6 CTAs per SM)
+    int threads = 256;
+    if (const char* e = getenv("SPK_FWD_THREADS")) threads = atoi(e) <= 128 ? 128 : 256;
+    size_t tile_target = threads == 128 ? 16 * 1024 : 32 * 1024;
+    if (const char* e = getenv("SPK_FWD_TILE_KB")) tile_target = (size_t)atoi(e) * 1024;
+    int T = (int)std::max<size_t>(1, std::min<size_t>(16, tile_target / row_bytes));
     while (T > 1 && fixed + 2 * (size_t)T * row_bytes > budget) --T;
     T = std::min(T, C);
     p.T = T;
     const size_t smem = fixed + 2 * (size_t)T * row_bytes;
-    if (smem > 48 * 1024)
-        SPK_CUDA(cudaFuncSetAttribute(sp_gather_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long grid = occupancy_slots((const void*)sp_gather_fwd_kernel, G_THREADS, smem, 0);
-    grid = std::min<long long>(grid, (p.rows + T - 1) / T);
-    SPK_CUDA(launch_k(sp_gather_fwd_kernel, dim3((int)grid), dim3(G_THREADS), smem, (cudaStream_t)stream, p));
+    auto launch = [&](auto kern, int nt) -> int {
+        if (smem > 48 * 1024)
+            SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long long grid = occupancy_slots((const void*)kern, nt, smem, 0);
+        grid = std::min<long long>(grid, (p.rows + T - 1) / T);
+        SPK_CUDA(launch_k(kern, dim3((int)grid), dim3(nt), smem, (cudaStream_t)stream, p));
+        return SPK_OK;
+    };
+    const int rc = threads == 128 ? launch(sp_gather_fwd_kernel<128>, 128) : launch(sp_gather_fwd_kernel<256>, 256);
+    if (rc != SPK_OK) return rc;
     if (want_cab && !p.cab_fast) {
         const long long n_rows = (long long)B * C * R;
         const long long total = n_rows * cab;

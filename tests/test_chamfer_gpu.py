@@ -260,3 +260,36 @@ def test_random_shapes_vs_oracle():
         tag = "trial %d: B=%d n=%d m=%d" % (trial, B, n, m)
         for x, y in zip(o, r):
             assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), tag
+
+
+@pytest.mark.parametrize("split", [1, 2, 5, 64])
+def test_split_jobs_are_bit_identical(split, monkeypatch):
+    """Sub-jobs over target ranges (used when the grid is underfilled) merge through a 64-bit atomicMin:
+    the result is the same first minimum, whatever the split."""
+    a, b = clouds(2, 3000, 5000, seed=split)
+    b[:, 4000:4100] = b[:, 100:200]                   # duplicates in different sub-jobs: the lower index wins
+    r = co.forward(a, b)
+    monkeypatch.setenv("SPK_TC_SPLIT", str(split))
+    o = cuda_forward(a, b)
+    for x, y in zip(o, r):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
+def test_cluster_backward_matches_two_kernel_form(monkeypatch):
+    """One cluster launch per call (default) against the two-launch form (pass A, pass B), on a size whose
+    points exceed what a cluster's threads hold in registers, and against the oracle."""
+    from softpool_b200 import ops
+    B, n, m = 2, 21000, 17001
+    a, b = clouds(B, n, m, seed=9)
+    rng = np.random.default_rng(2)
+    g1 = rng.random((B, n), dtype=np.float32); g2 = rng.random((B, m), dtype=np.float32)
+    t = lambda v: torch.from_numpy(v).to(dev())
+    d1, d2, i1, i2 = ops.chamfer_forward(t(a), t(b))
+    one = ops.chamfer_backward(t(a), t(b), t(g1), t(g2), i1, i2)
+    monkeypatch.setenv("SPK_CH_BWD_TWO_KERNELS", "1")
+    two = ops.chamfer_backward(t(a), t(b), t(g1), t(g2), i1, i2)
+    for x, y in zip(one, two):
+        torch.testing.assert_close(x, y, rtol=1e-4, atol=1e-7)
+    rg1, rg2 = co.backward(a, b, g1, g2, i1.cpu().numpy(), i2.cpu().numpy())
+    np.testing.assert_allclose(one[0].cpu().numpy(), rg1, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(one[1].cpu().numpy(), rg2, rtol=1e-4, atol=1e-6)

@@ -293,3 +293,40 @@ def test_backward_is_deterministic_and_without_cabins_grad():
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
     ref = torch.zeros_like(x).scatter_add_(2, idx.long().reshape(4, 1, -1).expand(4, 64, -1), g.reshape(4, 64, -1))
     torch.testing.assert_close(outs[0], ref, rtol=1e-4, atol=1e-5)
+
+
+PULL_SHAPES = [
+    # B, C, N, R, k, cab                what the backward takes
+    (2, 24, 2048, 8, 256, 8),          # pull, bulk tiles + bulk window-max gradient, two rows per group
+    (3, 10, 1000, 3, 50, 5),           # R*k % 4 != 0 and R*cab % 8 != 0: cooperative loads, register fold
+    (1, 5, 4099, 2, 4099, 7),          # odd N: scalar stores; every point selected by every region
+    (2, 7, 16384, 8, 2048, 8),         # large tables: one wide CTA per SM
+    (1, 3, 8192, 8, 8192, 8),          # R*k >= 65535: slots do not fit u16 -> the push kernel serves it
+    (2, 300, 512, 64, 8, 8),           # many regions, C not a multiple of the group
+]
+
+
+@pytest.mark.parametrize("B,C,N,R,k,cab", PULL_SHAPES)
+def test_backward_kernels_agree(B, C, N, R, k, cab, monkeypatch):
+    """The pull backward (default) and the shared-memory scatter backward (SPK_BWD=push) sum a point's
+    contributions in the same ascending-region order: bit-identical, and equal to autograd's scatter_add
+    within the stated tolerance."""
+    from softpool_b200 import ops
+    torch.manual_seed(B * 1000 + N + k)
+    x = torch.randn(B, C, N, device=dev(), requires_grad=True)
+    keys = torch.round(torch.randn(B, R, N, device=dev()) * 64) / 64           # plenty of ties
+    idx, _, _ = ops.softpool_topk(keys, k)
+    g1 = torch.randn(B, C, R, k, device=dev()); g2 = torch.randn(B, C, R, cab, device=dev())
+    res = {}
+    for mode in ("pull", "push"):
+        monkeypatch.setenv("SPK_BWD", mode)
+        cube, cabins = ops.softpool_gather(x, idx, cab)
+        (res[mode],) = torch.autograd.grad([cube, cabins], x, [g1, g2])
+    assert torch.equal(res["pull"].view(torch.int32), res["push"].view(torch.int32))
+    xr = x.detach().clone().requires_grad_(True)
+    li = idx.long()
+    cube_r = torch.gather(xr[:, :, None, :].expand(B, C, R, N), 3, li[:, None].expand(B, C, R, k))
+    wl = k // cab
+    cab_r = cube_r[..., :wl * cab].reshape(B, C, R, cab, wl).max(-1)[0]
+    torch.autograd.backward([cube_r, cab_r], [g1, g2])
+    torch.testing.assert_close(res["pull"], xr.grad, rtol=RTOL_GRAD, atol=1e-4)
