@@ -38,6 +38,8 @@ constexpr int TC_THREADS = 320;         // 10 warps
 constexpr int TC_SB_TILES = 8;          // tiles per super-block (1024 targets)
 constexpr int TC_SB_TARGETS = TC_SB_TILES * TC_TILE;
 constexpr int TC_CHUNK = 16;            // targets per filter chunk
+constexpr int TC_CM_WORDS = TC_SB_TARGETS / 32;   // packed words (2 chunk minima each) per query row and super-block
+constexpr int TC_MIN_WARPS = 4, TC_EXACT_WARPS = 4;
 constexpr int TC_TILE_BYTES = TC_TILE * 32;
 constexpr float TC_PAD_NORM = 30000.f;  // norm of padding targets: never the minimum
 
@@ -46,7 +48,8 @@ struct ChamferMeta {                    // per sample, written by the prep kerne
     float scale;                        // power of two: |(x - c) * scale| <= 1
     float tau;                          // filter slack in scaled squared units
     float scale2;                       // scale * scale
-    float pad0, pad1;
+    float bias;                         // power of two added to every approximate distance (keeps them > 0)
+    float nonfinite;                    // != 0: some coordinate is NaN/inf -> every chunk is evaluated exactly
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -66,8 +69,13 @@ __device__ __forceinline__ void split3(float v, __half& h, __half& m, __half& l)
 // byte offset of row r's first 16-byte K-chunk inside an operand array
 __device__ __forceinline__ size_t op_row_offset(int r) { return (size_t)(r >> 3) * 256 + (size_t)(r & 7) * 16; }
 
+// B rows are permuted inside every aligned group of 32 targets: target u of the group sits in row
+// ((u & 15) << 1) | (u >> 4), so that the EVEN accumulator columns of the group are targets 0..15 and the
+// ODD columns targets 16..31 -- the two 16-bit lanes of the packed minimum then hold two contiguous chunks.
+__device__ __forceinline__ int b_row_of(int r) { return (r & ~31) | ((r & 15) << 1) | ((r >> 4) & 1); }
+
 __device__ __forceinline__ void write_rows(unsigned char* opA, unsigned char* opB, int r, bool real,
-                                           float ux, float uy, float uz) {
+                                           float ux, float uy, float uz, float bias) {
     __align__(16) __half a[16];
     __align__(16) __half b[16];
     if (real) {
@@ -79,20 +87,20 @@ __device__ __forceinline__ void write_rows(unsigned char* opA, unsigned char* op
         a[0] = __hmul(m2, xh); a[1] = a[0]; a[2] = __hmul(m2, xl);
         a[3] = __hmul(m2, yh); a[4] = a[3]; a[5] = __hmul(m2, yl);
         a[6] = __hmul(m2, zh); a[7] = a[6]; a[8] = __hmul(m2, zl);
-        a[9] = nh; a[10] = nm; a[11] = nl; a[12] = one; a[13] = one; a[14] = one; a[15] = zero;
+        a[9] = nh; a[10] = nm; a[11] = nl; a[12] = one; a[13] = one; a[14] = one; a[15] = one;
         b[0] = xh; b[1] = xl; b[2] = xh; b[3] = yh; b[4] = yl; b[5] = yh; b[6] = zh; b[7] = zl; b[8] = zh;
-        b[9] = one; b[10] = one; b[11] = one; b[12] = nh; b[13] = nm; b[14] = nl; b[15] = zero;
+        b[9] = one; b[10] = one; b[11] = one; b[12] = nh; b[13] = nm; b[14] = nl; b[15] = __float2half_rn(bias);
     } else {
         const __half zero = __float2half_rn(0.f), one = __float2half_rn(1.f);
 #pragma unroll
         for (int i = 0; i < 16; ++i) { a[i] = zero; b[i] = zero; }
         b[9] = one; b[12] = __float2half_rn(TC_PAD_NORM);     // a padding target is "infinitely" far
     }
-    const size_t o = op_row_offset(r);
+    const size_t o = op_row_offset(r), ob = op_row_offset(b_row_of(r));
     *reinterpret_cast<uint4*>(opA + o) = *reinterpret_cast<const uint4*>(&a[0]);
     *reinterpret_cast<uint4*>(opA + o + 128) = *reinterpret_cast<const uint4*>(&a[8]);
-    *reinterpret_cast<uint4*>(opB + o) = *reinterpret_cast<const uint4*>(&b[0]);
-    *reinterpret_cast<uint4*>(opB + o + 128) = *reinterpret_cast<const uint4*>(&b[8]);
+    *reinterpret_cast<uint4*>(opB + ob) = *reinterpret_cast<const uint4*>(&b[0]);
+    *reinterpret_cast<uint4*>(opB + ob + 128) = *reinterpret_cast<const uint4*>(&b[8]);
 }
 
 struct PrepParams {
@@ -117,7 +125,8 @@ chamfer_prep_kernel(const PrepParams p) {
     // bounding box over both clouds (every CTA of the sample recomputes it: 12*(n+m) bytes from L2).
     // 128-bit loads, three per step = four whole points, so the axis of every lane is static.
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    auto upd = [&](int a, float v) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); };
+    int bad = 0;                                        // a NaN / inf coordinate anywhere in the sample
+    auto upd = [&](int a, float v) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); bad |= !(fabsf(v) < INFINITY); };
     for (int c = 0; c < 2; ++c) {
         const float* X = c ? Q : P;
         const int cnt = c ? p.m : p.n;
@@ -144,7 +153,7 @@ chamfer_prep_kernel(const PrepParams p) {
     if ((tid & 31) == 0)
 #pragma unroll
         for (int a = 0; a < 3; ++a) { red[a][tid >> 5] = lo[a]; red[3 + a][tid >> 5] = hi[a]; }
-    __syncthreads();
+    bad = __syncthreads_or(bad);
     if (tid == 0) {
         float L[3], H[3];
         for (int a = 0; a < 3; ++a) {
@@ -170,14 +179,20 @@ chamfer_prep_kernel(const PrepParams p) {
         const float e_tot = 7.62939453125e-6f + 16.f * delta;
         s_meta[0] = c[0]; s_meta[1] = c[1]; s_meta[2] = c[2]; s_meta[3] = scale;
         s_meta[4] = 2.f * e_tot; s_meta[5] = scale * scale;
+        // bias: a power of two above the error bound, so that every approximate distance is a POSITIVE fp16
+        // (its bit pattern then orders like its value); 2^-6 unless the coordinates are badly conditioned
+        float bias = 0.015625f;
+        while (bias < 4.f * e_tot && bias < 1024.f) bias *= 2.f;
+        s_meta[6] = bias;
         if (blockIdx.x == 0) {
             ChamferMeta mm; mm.cx = c[0]; mm.cy = c[1]; mm.cz = c[2]; mm.scale = scale; mm.tau = 2.f * e_tot;
-            mm.scale2 = scale * scale; mm.pad0 = 0.f; mm.pad1 = 0.f;
+            mm.scale2 = scale * scale; mm.bias = bias;
+            mm.nonfinite = (bad || !(bias >= 4.f * e_tot)) ? 1.f : 0.f;     // hopeless conditioning counts as non-finite
             p.meta[b] = mm;
         }
     }
     __syncthreads();
-    const float cx = s_meta[0], cy = s_meta[1], cz = s_meta[2], sc = s_meta[3];
+    const float cx = s_meta[0], cy = s_meta[1], cz = s_meta[2], sc = s_meta[3], bias = s_meta[6];
     unsigned char* A1 = p.A1 + (size_t)b * p.n_pad * 32; unsigned char* B1 = p.B1 + (size_t)b * p.n_pad * 32;
     unsigned char* A2 = p.A2 + (size_t)b * p.m_pad * 32; unsigned char* B2 = p.B2 + (size_t)b * p.m_pad * 32;
     const int total = p.n_pad + p.m_pad;
@@ -192,7 +207,7 @@ chamfer_prep_kernel(const PrepParams p) {
             raw.x = __ldg(s); raw.y = __ldg(s + 1); raw.z = __ldg(s + 2);
             ux = (raw.x - cx) * sc; uy = (raw.y - cy) * sc; uz = (raw.z - cz) * sc;
         }
-        write_rows(first ? A1 : A2, first ? B1 : B2, r, real, ux, uy, uz);
+        write_rows(first ? A1 : A2, first ? B1 : B2, r, real, ux, uy, uz, bias);
         (first ? p.T1 + (size_t)b * p.n_pad : p.T2 + (size_t)b * p.m_pad)[r] = raw;
         if (real && p.packed1 != nullptr)
             (first ? p.packed1 + (size_t)b * p.n : p.packed2 + (size_t)b * p.m)[r] = ~0ull;
@@ -217,8 +232,9 @@ __device__ __forceinline__ uint64_t umma_smem_desc(const void* smem_ptr) {
     d |= (uint64_t)1 << 46;
     return d;
 }
-// kind::f16: A, B = F16 (0), D = F32 (1), both K-major, M = 128, N = TC_N
-constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::f16: A, B = F16 (0), D = F16 (0: one fp16 per 32-bit TMEM column), both K-major, M = 128, N = TC_N.
+// A single K=16 instruction forms the whole distance, so the only fp16 rounding is the final one.
+constexpr uint32_t TC_IDESC = (0u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
     asm volatile(
@@ -258,6 +274,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 columns of fp16 accumulators -> 16 registers, two columns per register (even column in the low half)
+__device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// minimum of 16 packed words, per 16-bit lane (positive fp16 bit patterns order like their values):
+// VIMNMX3.U16x2, four new elements per instruction -- twice the rate of the fp32 FMNMX3 (tools/micro/minbench.cu)
+__device__ __forceinline__ uint32_t pmin16(const uint32_t* w) {
+    uint32_t m0 = __vimin3_u16x2(w[0], w[1], w[2]), m1 = __vimin3_u16x2(w[3], w[4], w[5]);
+    m0 = __vimin3_u16x2(m0, w[6], w[7]); m1 = __vimin3_u16x2(m1, w[8], w[9]);
+    m0 = __vimin3_u16x2(m0, w[10], w[11]); m1 = __vimin3_u16x2(m1, w[12], w[13]);
+    return __vimin3_u16x2(m0, m1, __vminu2(w[14], w[15]));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float min3(float a, float b, float c) {
     float r;
@@ -275,7 +309,7 @@ __device__ __forceinline__ float ref_sqdist_tc(float x1, float y1, float z1, flo
     const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void exact_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four exact warps
 
 // ---------------------------------------------------------------------------------------------
 // main kernel
@@ -296,10 +330,10 @@ struct __align__(128) TcSmem {
     unsigned char a_tile[2][TC_TILE_BYTES];                    // double-buffered: the next job's queries arrive early
     unsigned char b_tile[TC_STAGES][TC_TILE_BYTES];
     float4 t4[2][TC_SB_TARGETS];                               // raw target coordinates, per super-block
-    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full[2], a_empty[2], tmem_full[TC_NBUF], tmem_empty[TC_NBUF], t4_full[2], t4_empty[2];
+    uint32_t cm[2][TC_CM_WORDS * TC_TILE];                     // packed chunk minima of a super-block, [word][row]
+    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full[2], a_empty[2], tmem_full[TC_NBUF], tmem_empty[TC_NBUF], t4_full[2], t4_empty[2],
+             cm_full[2], cm_empty[2];
     uint32_t tmem_base;
-    float rowmin[2][2][TC_TILE];          // [super-block parity][column half][row]
-    float best_d[TC_TILE]; int best_i[TC_TILE];
     int dbg[2];
     int last;                             // split jobs: this CTA finished the query tile's last sub-job
 };
@@ -322,8 +356,9 @@ chamfer_tc_kernel(const TcParams p) {
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1); }
-        for (int i = 0; i < TC_NBUF; ++i) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], 8); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&S.t4_full[i], 1); mbar_init(&S.t4_empty[i], 8); }
+        for (int i = 0; i < TC_NBUF; ++i) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], TC_MIN_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&S.t4_full[i], 1); mbar_init(&S.t4_empty[i], TC_EXACT_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&S.cm_full[i], TC_MIN_WARPS); mbar_init(&S.cm_empty[i], TC_EXACT_WARPS); }
         fence_mbar_init();
 #ifdef SPK_TIMING
         S.dbg[0] = 0; S.dbg[1] = 0;
@@ -341,7 +376,7 @@ chamfer_tc_kernel(const TcParams p) {
     const long long tk0 = clock64();
     __shared__ long long tlog_t[96]; __shared__ int tlog_a[96]; __shared__ int tlog_b[96]; __shared__ const char* tlog_s[96]; __shared__ int tlog_n;
     if (tid == 0) tlog_n = 0;
-#define TCLOG(tag, a, b) do { if (blockIdx.x == 0 && warp == 2 && lane == 0 && tlog_n < 96) { tlog_t[tlog_n] = clock64() - tk0; tlog_s[tlog_n] = tag; tlog_a[tlog_n] = (int)(a); tlog_b[tlog_n] = (int)(b); ++tlog_n; } } while (0)
+#define TCLOG(tag, a, b) do { if (blockIdx.x == 0 && (warp == 2 || warp == 6) && lane == 0) { const int ti_ = atomicAdd(&tlog_n, 1); if (ti_ < 96) { tlog_t[ti_] = clock64() - tk0; tlog_s[ti_] = tag; tlog_a[ti_] = (int)(a) + 1000 * (warp == 6); tlog_b[ti_] = (int)(b); } } } while (0)
 #else
 #define TCLOG(tag, a, b)
 #endif
@@ -382,15 +417,17 @@ chamfer_tc_kernel(const TcParams p) {
                 for (int sb = 0; sb < n_sb; ++sb) {
                     const uint32_t sbi = sb_it + sb, pb = sbi & 1;
                     constexpr int tiles = TC_SB_TILES;
-                    mbar_wait(&S.t4_empty[pb], (uint32_t)(((sbi >> 1) & 1) ^ 1));
-                    mbar_expect_tx(&S.t4_full[pb], (uint32_t)tiles * TC_TILE * 16u);
-                    bulk_g2s(S.t4[pb], T4 + (size_t)sb * TC_SB_TARGETS, (uint32_t)tiles * TC_TILE * 16u, &S.t4_full[pb]);
                     for (int tt = 0; tt < tiles; ++tt) {
                         const uint32_t it = ring_it + sb * TC_SB_TILES + tt, s = it % TC_STAGES;
                         mbar_wait(&S.empty[s], (uint32_t)(((it / TC_STAGES) & 1) ^ 1));
                         mbar_expect_tx(&S.full[s], TC_TILE_BYTES);
                         bulk_g2s(S.b_tile[s], Bop + (size_t)(sb * TC_SB_TILES + tt) * TC_TILE_BYTES, TC_TILE_BYTES, &S.full[s]);
                     }
+                    // raw coordinates for the exact pass: after the operand tiles, so that the exact warps (which
+                    // lag up to two super-blocks behind the MMAs) never hold the operand stream back
+                    mbar_wait(&S.t4_empty[pb], (uint32_t)(((sbi >> 1) & 1) ^ 1));
+                    mbar_expect_tx(&S.t4_full[pb], (uint32_t)tiles * TC_TILE * 16u);
+                    bulk_g2s(S.t4[pb], T4 + (size_t)sb * TC_SB_TARGETS, (uint32_t)tiles * TC_TILE * 16u, &S.t4_full[pb]);
                 }
             }
         } else if (warp == 1) {
@@ -414,32 +451,20 @@ chamfer_tc_kernel(const TcParams p) {
                 }
                 umma_commit(&S.a_empty[ab]);             // this A buffer may be replaced
             }
-        } else {
-            // ===== epilogue: 8 warps; warp%4 picks the TMEM lane quarter, (warp-2)/4 the column half =====
-            const int q = warp & 3, h = (warp - 2) >> 2;
-            const int row = q * 32 + lane;                         // query row inside the tile
-            const int gq = job * TC_TILE + row;                    // query index inside the cloud
-            const bool live = gq < nq;
-            const float* Qx = (dir ? p.xyz2 : p.xyz1) + (size_t)b * nq * 3;
-            const float* Tx = (dir ? p.xyz1 : p.xyz2) + (size_t)b * nt * 3;
-            const float tau = p.meta[b].tau, scale2 = p.meta[b].scale2;
-            float qx = 0.f, qy = 0.f, qz = 0.f;
-            if (live) { qx = __ldg(Qx + 3 * (size_t)gq); qy = __ldg(Qx + 3 * (size_t)gq + 1); qz = __ldg(Qx + 3 * (size_t)gq + 2); }
-            // reference: the first target initialises the running best (`k==0 || d<best`, chamfer.cu:36).
-            // The loads are issued here, the distance is formed at the first filter: their latency hides
-            // behind the first super-block's min pass.
-            const int t_first = sb0 * TC_SB_TARGETS;                // first target of this (sub-)job: always a real point
-            const float t0x = __ldg(Tx + 3 * (size_t)t_first), t0y = __ldg(Tx + 3 * (size_t)t_first + 1), t0z = __ldg(Tx + 3 * (size_t)t_first + 2);
-            float best_d = 0.f;
-            int best_i = t_first;
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * (TC_N / 2);
+        } else if (warp < 2 + TC_MIN_WARPS) {
+            // ===== min warps (4, one per TMEM lane quarter): accumulators -> packed chunk minima -> shared memory.
+            // They never wait for the filter / exact pass, so the TMEM read path -- the resource that paces this
+            // kernel -- stays busy; the exact warps follow up to two super-blocks behind.
+            const int q = warp & 3;
+            const int row = q * 32 + lane;                         // query row inside the tile = TMEM lane
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+            constexpr int ACC_PER_SB = TC_SB_TARGETS / TC_N;
+            constexpr int WPA = TC_N / 32;                         // packed words per accumulator and row
             TCLOG("job start", job_id, n_sb);
-
             for (int sb = 0; sb < n_sb; ++sb) {
-                // per thread: TC_N/2 columns of every accumulator = TC_N/32 chunks of 16 targets
-                constexpr int CPA = TC_N / 32;                              // chunks per accumulator per thread
-                constexpr int ACC_PER_SB = TC_SB_TARGETS / TC_N;
-                float cm[CPA * ACC_PER_SB];
+                const uint32_t sbi = sb_it + sb, pb = sbi & 1;
+                mbar_wait(&S.cm_empty[pb], (uint32_t)(((sbi >> 1) & 1) ^ 1));   // the exact warps have read this buffer
+                uint32_t* out = S.cm[pb] + row;
 #pragma unroll
                 for (int a = 0; a < ACC_PER_SB; ++a) {
                     const uint32_t ai = acc_it + (uint32_t)(sb * ACC_PER_SB + a), buf = ai % TC_NBUF;
@@ -447,51 +472,96 @@ chamfer_tc_kernel(const TcParams p) {
                     if (a == 0) TCLOG(" sb first acc ready", sb, 0);
                     tc_fence_after();
                     const uint32_t ta = lane_addr + buf * TC_N;
-                    float va[16], vb[16];
-                    tmem_ld16(ta, va);
-                    tmem_ld16(ta + 16, vb);
+                    uint32_t w0[16], w1[16], w2[16], w3[16];       // 4 x 32 columns of fp16 accumulators, two per register
+                    tmem_ld16p(ta, w0); tmem_ld16p(ta + 32, w1); tmem_ld16p(ta + 64, w2); tmem_ld16p(ta + 96, w3);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < CPA; c += 2) {
-                        cm[CPA * a + c] = min16(va);
-                        if (c + 2 < CPA) tmem_ld16(ta + 16 * (c + 2), va);
-                        cm[CPA * a + c + 1] = min16(vb);
-                        if (c + 2 < CPA) { tmem_ld16(ta + 16 * (c + 3), vb); tmem_ld_wait(); }
-                    }
+                    // the values are in registers: hand the accumulator back before reducing them
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&S.tmem_empty[buf]);      // accumulator buffer may be overwritten
+                    if (lane == 0) mbar_arrive(&S.tmem_empty[buf]);
+                    out[(WPA * a + 0) * TC_TILE] = pmin16(w0);
+                    out[(WPA * a + 1) * TC_TILE] = pmin16(w1);
+                    out[(WPA * a + 2) * TC_TILE] = pmin16(w2);
+                    out[(WPA * a + 3) * TC_TILE] = pmin16(w3);
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.cm_full[pb]);          // release: the warp's minima are visible to the exact warps
                 TCLOG(" sb min pass done", sb, 0);
-                // ---- filter: chunks within tau of the row minimum (or of the exact best so far) ----
-                constexpr int NCM = CPA * ACC_PER_SB;                       // 32
-                float rmin = min3(cm[0], cm[1], cm[2]);
+            }
+        } else {
+            // ===== exact warps (4): one thread per query row: filter the chunk minima, re-evaluate the survivors =====
+            const int q = warp & 3;
+            const int row = q * 32 + lane;                         // query row inside the tile
+            const int gq = job * TC_TILE + row;                    // query index inside the cloud
+            const bool live = gq < nq;
+            const float* Qx = (dir ? p.xyz2 : p.xyz1) + (size_t)b * nq * 3;
+            const float* Tx = (dir ? p.xyz1 : p.xyz2) + (size_t)b * nt * 3;
+            const ChamferMeta mt = p.meta[b];
+            const float tau = mt.tau, scale2 = mt.scale2, bias = mt.bias;
+            const bool eval_all = mt.nonfinite != 0.f;
+            float qx = 0.f, qy = 0.f, qz = 0.f;
+            if (live) { qx = __ldg(Qx + 3 * (size_t)gq); qy = __ldg(Qx + 3 * (size_t)gq + 1); qz = __ldg(Qx + 3 * (size_t)gq + 2); }
+            // reference: the first target initialises the running best (`k==0 || d<best`, chamfer.cu:36)
+            const int t_first = sb0 * TC_SB_TARGETS;                // first target of this (sub-)job: always a real point
+            const float t0x = __ldg(Tx + 3 * (size_t)t_first), t0y = __ldg(Tx + 3 * (size_t)t_first + 1), t0z = __ldg(Tx + 3 * (size_t)t_first + 2);
+            float best_d = 0.f;
+            int best_i = t_first;
+
+            for (int sb = 0; sb < n_sb; ++sb) {
+                const uint32_t sbi = sb_it + sb, pb = sbi & 1;
+                constexpr int NW = TC_CM_WORDS;                             // 32 words = 64 chunk minima per row
+                uint32_t cm[NW];
+                mbar_wait(&S.cm_full[pb], (uint32_t)((sbi >> 1) & 1));
+                {
+                    const uint32_t* in = S.cm[pb] + row;
 #pragma unroll
-                for (int i = 3; i + 1 < NCM; i += 2) rmin = min3(rmin, cm[i], cm[i + 1]);
-                rmin = fminf(rmin, cm[NCM - 1]);
-                S.rowmin[sb & 1][h][row] = rmin;
-                epi_bar();
-                rmin = fminf(rmin, S.rowmin[sb & 1][h ^ 1][row]);
+                    for (int i = 0; i < NW; ++i) cm[i] = in[i * TC_TILE];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.cm_empty[pb]);             // in registers: the buffer may be refilled
+                // ---- filter: chunks whose minimum is within the error slack of the row minimum (or of the
+                // exact best so far).  Everything is a positive fp16 pattern: 15-bit unsigned compares.
+                uint32_t rm = __vimin3_u16x2(cm[0], cm[1], cm[2]);
+#pragma unroll
+                for (int i = 3; i + 1 < NW; i += 2) rm = __vimin3_u16x2(rm, cm[i], cm[i + 1]);
+                rm = __vminu2(rm, cm[NW - 1]);
+                const uint32_t r16 = min(rm & 0xFFFFu, rm >> 16);
                 if (sb == 0) best_d = ref_sqdist_tc(qx, qy, qz, t0x, t0y, t0z);
-                float thr = fminf(rmin, best_d * scale2) + tau;
-                if (!(thr == thr)) thr = INFINITY;                       // NaN anywhere: evaluate everything
-                uint32_t mask = 0;
+                // threshold: min(row minimum, exact best) widened by the fp16 rounding of the accumulator
+                // (relative, 2^-8 = 4 ulp) and the error bound of the operands (absolute, tau), rounded UP to fp16
+                float thr = fminf(__half2float(__ushort_as_half((unsigned short)r16)), fmaf(best_d, scale2, bias));
+                thr = fmaf(thr, 1.00390625f, tau);
+                uint32_t t16 = (uint32_t)__half_as_ushort(__float2half_ru(thr));
+                if (!(thr == thr) || t16 > 0x7FFFu) t16 = 0x7FFFu;       // NaN / negative garbage: evaluate everything
+                // mask bit i (i < 16): chunk in the low lane of word i, bit 16+i: its high lane; words 16..31 in the upper half
+                uint32_t m_lo = 0, m_hi = 0;
+                if (eval_all) {
+                    m_lo = m_hi = 0xFFFFFFFFu;
+                } else {
+                    // per lane (0x8000 | t) - c keeps bit 15 exactly when c <= t (both are 15-bit values: no borrow
+                    // crosses the lanes); the bits 15 / 31 of word i go to mask bits i / 16+i
+                    const uint32_t T2 = (t16 * 0x10001u) | 0x80008000u;
 #pragma unroll
-                for (int i = 0; i < NCM; ++i) if (!(cm[i] > thr)) mask |= 1u << i;     // NaN minima pass too
-                if (!live) mask = 0;
+                    for (int i = 0; i < 16; ++i) {
+                        m_lo |= ((T2 - cm[i]) >> (15 - i)) & (0x10001u << i);
+                        m_hi |= ((T2 - cm[16 + i]) >> (15 - i)) & (0x10001u << i);
+                    }
+                }
+                unsigned long long mask = live ? (((unsigned long long)m_hi << 32) | m_lo) : 0ull;
 #ifdef SPK_TIMING
-                atomicAdd(&S.dbg[0], __popc(mask)); atomicAdd(&S.dbg[1], live ? 1 : 0);
+                atomicAdd(&S.dbg[0], __popcll(mask)); atomicAdd(&S.dbg[1], live ? 1 : 0);
 #endif
                 // ---- exact float32 re-evaluation of the surviving chunks (reference expression) ----
-                const uint32_t sbi = sb_it + sb, pb = sbi & 1;
                 mbar_wait(&S.t4_full[pb], (uint32_t)((sbi >> 1) & 1));
                 const float4* tsm = S.t4[pb];
-                TCLOG(" sb filter done, t4 ready", sb, __popc(mask));
+                TCLOG(" sb filter done, t4 ready", sb, __popcll(mask));
                 const int sb_base = (sb0 + sb) * TC_SB_TARGETS;
                 while (mask) {
-                    const int i = __ffs(mask) - 1;
+                    const int pbit = __ffsll((long long)mask) - 1;
                     mask &= mask - 1;
-                    const int l0 = (i / CPA) * TC_N + h * (TC_N / 2) + (i % CPA) * TC_CHUNK;   // inside the super-block
+                    // word w -> accumulator w / 4, 32-column group w % 4; the high lane holds the odd columns = targets 16..31
+                    const int w = ((pbit >> 5) << 4) | (pbit & 15), hi = (pbit >> 4) & 1;
+                    const int l0 = w * 32 + hi * TC_CHUNK;                  // inside the super-block
                     // every chunk starts on a 256-byte boundary: rotate the visiting order by the lane so
                     // that the 8 lanes of a quarter-warp hit 8 different bank groups (no LDS.128 conflicts).
                     // All 16 exact distances first (FMA pipe), then ONE min tree and the lowest offset that
@@ -516,12 +586,7 @@ chamfer_tc_kernel(const TcParams p) {
                 if (lane == 0) mbar_arrive(&S.t4_empty[pb]);
                 TCLOG(" sb exact done", sb, 0);
             }
-            // ---- merge the two column halves of each row, first minimum wins ----
-            if (h == 1) { S.best_d[row] = best_d; S.best_i[row] = best_i; }
-            epi_bar();
-            if (h == 0 && live) {
-                const float d2 = S.best_d[row]; const int i2 = S.best_i[row];
-                if (d2 < best_d || (d2 == best_d && i2 < best_i)) { best_d = d2; best_i = i2; }
+            if (live) {
                 if (NS == 1) {
                     ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = best_d;
                     ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = best_i;
@@ -534,23 +599,24 @@ chamfer_tc_kernel(const TcParams p) {
             }
             if (NS > 1) {
                 // the sub-job that arrives last at the query tile's counter unpacks the merged minima.
-                // Ordering: the CTA barrier orders the threads' atomics before the elected thread's
+                // Ordering: the barrier orders the threads' atomics before the elected thread's
                 // acq_rel increment (release, cumulative); the last arriver's increment acquires every
                 // earlier sub-job's minima, the second barrier hands that to its other threads.
-                epi_bar();
-                if (warp == 2 && lane == 0) {
+                exact_bar();
+                if (warp == 2 + TC_MIN_WARPS && lane == 0) {
                     int* cnt = p.counters + (size_t)b * (p.tiles1 + p.tiles2) + (dir ? p.tiles1 : 0) + job;
                     int old;
                     asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(cnt) : "memory");
                     S.last = (old == NS - 1);
                 }
-                epi_bar();
-                if (S.last && h == 0 && live) {
+                exact_bar();
+                if (S.last && live) {
                     unsigned long long v;
                     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"((dir ? p.packed2 : p.packed1) + (size_t)b * nq + gq) : "memory");
                     ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = __uint_as_float((unsigned)(v >> 32));
                     ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = (int)(unsigned)v;
                 }
+                exact_bar();                                       // S.last is rewritten by the next split job
             }
         }
         if (warp >= 2) TCLOG("job end", job_id, 0);
@@ -559,7 +625,7 @@ chamfer_tc_kernel(const TcParams p) {
 
 #ifdef SPK_TIMING
     __syncthreads();
-    if (tid == 0 && blockIdx.x == 0) for (int i = 0; i < tlog_n; ++i) printf("  t=%7lld %s %d %d\n", tlog_t[i], tlog_s[i], tlog_a[i], tlog_b[i]);
+    if (tid == 0 && blockIdx.x == 0) for (int i = 0; i < min(tlog_n, 96); ++i) printf("  t=%7lld %s %d %d\n", tlog_t[i], tlog_s[i], tlog_a[i], tlog_b[i]);
     if (tid == 0 && blockIdx.x < 2) printf("tc cta %d: chunks evaluated %d over %d (row, half, super-block) filters = %.3f each\n", blockIdx.x, S.dbg[0], S.dbg[1], (float)S.dbg[0] / (float)max(S.dbg[1], 1));
 #endif
     tc_fence_before();
