@@ -27,12 +27,20 @@
 // (8-row x 16-byte core matrices, LBO = 128 B, SBO = 256 B), so tiles move with 1-D bulk copies.
 #include "spk_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
+
+#ifndef SPK_SPIN
+#define SPK_SPIN 0
+#endif
 
 namespace spk {
 
 constexpr int TC_TILE = 128;            // queries per CTA = targets per shared-memory B tile
-constexpr int TC_N = 128;               // targets per MMA (accumulator buffer width, TMEM columns)
-constexpr int TC_NBUF = 2;              // accumulator buffers: hides the release -> MMA -> commit round trip
+#ifndef SPK_TC_N
+#define SPK_TC_N 128
+#endif
+constexpr int TC_N = SPK_TC_N;          // targets per MMA (accumulator buffer width, TMEM columns)
+constexpr int TC_NBUF = 256 / TC_N;              // accumulator buffers: hides the release -> MMA -> commit round trip
 constexpr int TC_STAGES = 4;            // B-tile ring depth
 constexpr int TC_THREADS = 320;         // 10 warps
 constexpr int TC_SB_TILES = 8;          // tiles per super-block (1024 targets)
@@ -40,6 +48,7 @@ constexpr int TC_SB_TARGETS = TC_SB_TILES * TC_TILE;
 constexpr int TC_CHUNK = 16;            // targets per filter chunk
 constexpr int TC_CM_WORDS = TC_SB_TARGETS / 32;   // packed words (2 chunk minima each) per query row and super-block
 constexpr int TC_MIN_WARPS = 4, TC_EXACT_WARPS = 4;
+constexpr int TC_T4_BUFS = 2;           // raw-coordinate buffers: the exact warps lag the operand stream by up to two super-blocks
 constexpr int TC_TILE_BYTES = TC_TILE * 32;
 constexpr float TC_PAD_NORM = 30000.f;  // norm of padding targets: never the minimum
 
@@ -329,9 +338,9 @@ struct TcParams {
 struct __align__(128) TcSmem {
     unsigned char a_tile[2][TC_TILE_BYTES];                    // double-buffered: the next job's queries arrive early
     unsigned char b_tile[TC_STAGES][TC_TILE_BYTES];
-    float4 t4[2][TC_SB_TARGETS];                               // raw target coordinates, per super-block
+    float4 t4[TC_T4_BUFS][TC_SB_TARGETS];                      // raw target coordinates, per super-block
     uint32_t cm[2][TC_CM_WORDS * TC_TILE];                     // packed chunk minima of a super-block, [word][row]
-    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full[2], a_empty[2], tmem_full[TC_NBUF], tmem_empty[TC_NBUF], t4_full[2], t4_empty[2],
+    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full[2], a_empty[2], tmem_full[TC_NBUF], tmem_empty[TC_NBUF], t4_full[TC_T4_BUFS], t4_empty[TC_T4_BUFS],
              cm_full[2], cm_empty[2];
     uint32_t tmem_base;
     int dbg[2];
@@ -357,7 +366,7 @@ chamfer_tc_kernel(const TcParams p) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1); }
         for (int i = 0; i < TC_NBUF; ++i) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], TC_MIN_WARPS); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&S.t4_full[i], 1); mbar_init(&S.t4_empty[i], TC_EXACT_WARPS); }
+        for (int i = 0; i < TC_T4_BUFS; ++i) { mbar_init(&S.t4_full[i], 1); mbar_init(&S.t4_empty[i], TC_EXACT_WARPS); }
         for (int i = 0; i < 2; ++i) { mbar_init(&S.cm_full[i], TC_MIN_WARPS); mbar_init(&S.cm_empty[i], TC_EXACT_WARPS); }
         fence_mbar_init();
 #ifdef SPK_TIMING
@@ -374,11 +383,13 @@ chamfer_tc_kernel(const TcParams p) {
     tc_fence_after();
 #ifdef SPK_TIMING
     const long long tk0 = clock64();
-    __shared__ long long tlog_t[96]; __shared__ int tlog_a[96]; __shared__ int tlog_b[96]; __shared__ const char* tlog_s[96]; __shared__ int tlog_n;
+    __shared__ long long tlog_t[320]; __shared__ int tlog_a[320]; __shared__ int tlog_b[320]; __shared__ const char* tlog_s[320]; __shared__ int tlog_n;
     if (tid == 0) tlog_n = 0;
-#define TCLOG(tag, a, b) do { if (blockIdx.x == 0 && (warp == 2 || warp == 6) && lane == 0) { const int ti_ = atomicAdd(&tlog_n, 1); if (ti_ < 96) { tlog_t[ti_] = clock64() - tk0; tlog_s[ti_] = tag; tlog_a[ti_] = (int)(a) + 1000 * (warp == 6); tlog_b[ti_] = (int)(b); } } } while (0)
+#define TCLOG(tag, a, b) do { if (blockIdx.x == 0 && (warp == 2 || warp == 6) && lane == 0) { const int ti_ = atomicAdd(&tlog_n, 1); if (ti_ < 320) { tlog_t[ti_] = clock64() - tk0; tlog_s[ti_] = tag; tlog_a[ti_] = (int)(a) + 1000 * (warp == 6); tlog_b[ti_] = (int)(b); } } } while (0)
+#define TCLOGF(tag, a, b) do { if (blockIdx.x == 0 && lane == 0 && job_it == 1) { const int ti_ = atomicAdd(&tlog_n, 1); if (ti_ < 320) { tlog_t[ti_] = clock64() - tk0; tlog_s[ti_] = tag; tlog_a[ti_] = (int)(a); tlog_b[ti_] = (int)(b); } } } while (0)
 #else
 #define TCLOG(tag, a, b)
+#define TCLOGF(tag, a, b)
 #endif
     const uint32_t tmem_base = S.tmem_base;
     pdl_wait();                  // operands / metadata come from chamfer_prep_kernel
@@ -425,9 +436,10 @@ chamfer_tc_kernel(const TcParams p) {
                     }
                     // raw coordinates for the exact pass: after the operand tiles, so that the exact warps (which
                     // lag up to two super-blocks behind the MMAs) never hold the operand stream back
-                    mbar_wait(&S.t4_empty[pb], (uint32_t)(((sbi >> 1) & 1) ^ 1));
-                    mbar_expect_tx(&S.t4_full[pb], (uint32_t)tiles * TC_TILE * 16u);
-                    bulk_g2s(S.t4[pb], T4 + (size_t)sb * TC_SB_TARGETS, (uint32_t)tiles * TC_TILE * 16u, &S.t4_full[pb]);
+                    const uint32_t tb = sbi % TC_T4_BUFS;
+                    mbar_wait(&S.t4_empty[tb], (uint32_t)(((sbi / TC_T4_BUFS) & 1) ^ 1));
+                    mbar_expect_tx(&S.t4_full[tb], (uint32_t)tiles * TC_TILE * 16u);
+                    bulk_g2s(S.t4[tb], T4 + (size_t)sb * TC_SB_TARGETS, (uint32_t)tiles * TC_TILE * 16u, &S.t4_full[tb]);
                 }
             }
         } else if (warp == 1) {
@@ -438,14 +450,24 @@ chamfer_tc_kernel(const TcParams p) {
                 const uint64_t a_desc = umma_smem_desc(S.a_tile[ab]);
                 for (int t = 0; t < T; ++t) {
                     const uint32_t it = ring_it + t, s = it % TC_STAGES;
+#if SPK_SPIN >= 1
+                    mbar_wait_spin(&S.full[s], (uint32_t)((it / TC_STAGES) & 1));
+#else
                     mbar_wait(&S.full[s], (uint32_t)((it / TC_STAGES) & 1));
+#endif
 #pragma unroll
                     for (int half = 0; half < TC_TILE / TC_N; ++half) {     // TC_TILE / TC_N MMAs per 128-target smem tile
                         const uint32_t ai = acc_it + (TC_TILE / TC_N) * t + half, buf = ai % TC_NBUF;
+#if SPK_SPIN >= 1
+                        mbar_wait_spin(&S.tmem_empty[buf], (uint32_t)(((ai / TC_NBUF) & 1) ^ 1));
+#else
                         mbar_wait(&S.tmem_empty[buf], (uint32_t)(((ai / TC_NBUF) & 1) ^ 1));
+#endif
+                        TCLOGF("M empty ok", ai, 0);
                         tc_fence_after();
                         umma_f16(tmem_base + buf * TC_N, a_desc, umma_smem_desc(S.b_tile[s] + half * (TC_N * 32)), TC_IDESC);
                         umma_commit(&S.tmem_full[buf]);  // accumulator ready for the epilogue
+                        TCLOGF("M issued+commit", ai, 0);
                     }
                     umma_commit(&S.empty[s]);            // smem slot free once both MMAs have read it
                 }
@@ -468,21 +490,27 @@ chamfer_tc_kernel(const TcParams p) {
 #pragma unroll
                 for (int a = 0; a < ACC_PER_SB; ++a) {
                     const uint32_t ai = acc_it + (uint32_t)(sb * ACC_PER_SB + a), buf = ai % TC_NBUF;
+#if SPK_SPIN >= 2
+                    mbar_wait_spin(&S.tmem_full[buf], (ai / TC_NBUF) & 1);
+#else
                     mbar_wait(&S.tmem_full[buf], (ai / TC_NBUF) & 1);
+#endif
                     if (a == 0) TCLOG(" sb first acc ready", sb, 0);
+                    if (warp == 2) TCLOGF("E full ok", ai, 0);
                     tc_fence_after();
                     const uint32_t ta = lane_addr + buf * TC_N;
-                    uint32_t w0[16], w1[16], w2[16], w3[16];       // 4 x 32 columns of fp16 accumulators, two per register
-                    tmem_ld16p(ta, w0); tmem_ld16p(ta + 32, w1); tmem_ld16p(ta + 64, w2); tmem_ld16p(ta + 96, w3);
+                    uint32_t wv[WPA][16];                          // WPA x 32 columns of fp16 accumulators, two per register
+#pragma unroll
+                    for (int g = 0; g < WPA; ++g) tmem_ld16p(ta + 32 * g, wv[g]);
                     tmem_ld_wait();
+                    if (warp == 2) TCLOGF("E ld done", ai, 0);
                     // the values are in registers: hand the accumulator back before reducing them
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.tmem_empty[buf]);
-                    out[(WPA * a + 0) * TC_TILE] = pmin16(w0);
-                    out[(WPA * a + 1) * TC_TILE] = pmin16(w1);
-                    out[(WPA * a + 2) * TC_TILE] = pmin16(w2);
-                    out[(WPA * a + 3) * TC_TILE] = pmin16(w3);
+                    if (warp == 2) TCLOGF("E arrived", ai, 0);
+#pragma unroll
+                    for (int g = 0; g < WPA; ++g) out[(WPA * a + g) * TC_TILE] = pmin16(wv[g]);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.cm_full[pb]);          // release: the warp's minima are visible to the exact warps
@@ -552,8 +580,9 @@ chamfer_tc_kernel(const TcParams p) {
                 atomicAdd(&S.dbg[0], __popcll(mask)); atomicAdd(&S.dbg[1], live ? 1 : 0);
 #endif
                 // ---- exact float32 re-evaluation of the surviving chunks (reference expression) ----
-                mbar_wait(&S.t4_full[pb], (uint32_t)((sbi >> 1) & 1));
-                const float4* tsm = S.t4[pb];
+                const uint32_t tb = sbi % TC_T4_BUFS;
+                mbar_wait(&S.t4_full[tb], (uint32_t)((sbi / TC_T4_BUFS) & 1));
+                const float4* tsm = S.t4[tb];
                 TCLOG(" sb filter done, t4 ready", sb, __popcll(mask));
                 const int sb_base = (sb0 + sb) * TC_SB_TARGETS;
                 while (mask) {
@@ -583,7 +612,7 @@ chamfer_tc_kernel(const TcParams p) {
                     if (rmin_off < TC_CHUNK && (dmin < best_d || (dmin == best_d && t < best_i))) { best_d = dmin; best_i = t; }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&S.t4_empty[pb]);
+                if (lane == 0) mbar_arrive(&S.t4_empty[tb]);
                 TCLOG(" sb exact done", sb, 0);
             }
             if (live) {
@@ -625,7 +654,7 @@ chamfer_tc_kernel(const TcParams p) {
 
 #ifdef SPK_TIMING
     __syncthreads();
-    if (tid == 0 && blockIdx.x == 0) for (int i = 0; i < min(tlog_n, 96); ++i) printf("  t=%7lld %s %d %d\n", tlog_t[i], tlog_s[i], tlog_a[i], tlog_b[i]);
+    if (tid == 0 && blockIdx.x == 0) for (int i = 0; i < min(tlog_n, 320); ++i) printf("  t=%7lld %s %d %d\n", tlog_t[i], tlog_s[i], tlog_a[i], tlog_b[i]);
     if (tid == 0 && blockIdx.x < 2) printf("tc cta %d: chunks evaluated %d over %d (row, half, super-block) filters = %.3f each\n", blockIdx.x, S.dbg[0], S.dbg[1], (float)S.dbg[0] / (float)max(S.dbg[1], 1));
 #endif
     tc_fence_before();
@@ -705,7 +734,8 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
     const size_t smem = std::max(sizeof(TcSmem) + 128, (size_t)80 * 1024);
     SPK_CUDA(cudaFuncSetAttribute(chamfer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long jobs = ((long long)tp.tiles1 * S1 + (long long)tp.tiles2 * S2) * B;
-    const int grid = (int)std::min<long long>(jobs, 2LL * sm_count());         // persistent: 2 CTAs per SM
+    int grid = (int)std::min<long long>(jobs, 2LL * sm_count());         // persistent: 2 CTAs per SM
+    if (const char* e = getenv("SPK_TC_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
     SPK_CUDA(launch_k(chamfer_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tp));
     return SPK_OK;
 }
