@@ -53,12 +53,24 @@ def load_peaks():
 
 def load_traffic(workload):
     """ncu-measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one
-    `ncu --set full` capture, profiles/r1_traffic.json); {} when that workload was not captured."""
+    `ncu --set full` capture, profiles/r1_traffic.json, written by tools/ncu_traffic.py); {} when that
+    workload was not captured."""
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if not os.path.exists(p):
         return {}
-    d = json.load(open(p)).get({"A": "A", "A1": "A1"}.get(workload, workload), {})
+    d = json.load(open(p)).get(workload, {})
     return {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in d.items()}
+
+
+def traffic_of(traffic, *prefixes):
+    """Sum of the captured kernels whose name starts with one of the prefixes; None if one is missing."""
+    tot = 0.0
+    for pre in prefixes:
+        hit = [v for k, v in traffic.items() if k.startswith(pre)]
+        if not hit:
+            return None
+        tot += sum(hit)
+    return tot
 
 
 def algorithmic_bytes(w):
@@ -287,8 +299,8 @@ def run_b200(args, w, rank, local_rank, world):
             kern_us[name] = k0.elapsed_time(k1) * 1e3 / (5 * reps)
     fwd_b, bwd_b = algorithmic_bytes(w)
     traffic = load_traffic(args.workload)
-    tr_sp = sum(traffic.get(k, float("nan")) for k in ("sp_topk_kernel", "sp_gather_fwd_kernel", "sp_gather_bwd_kernel")) if traffic else None
-    tr_ch = (traffic.get("chamfer_prep_kernel", 0.0) + traffic.get("chamfer_tc_kernel", float("nan"))) if traffic else None
+    tr_sp = traffic_of(traffic, "sp_topk", "sp_gather_fwd", "sp_gather_bwd") if traffic else None
+    tr_ch = traffic_of(traffic, "chamfer_prep", "chamfer_tc") if traffic else None
     P = B * N * N
     sp_us = kern_us["sp_topk_f32"] + kern_us["sp_gather_fwd_f32"] + kern_us["sp_gather_bwd_f32"]
     ch_us = kern_us["chamfer_fwd_f32"] + kern_us["chamfer_loss_f32"] + kern_us["chamfer_bwd_f32"]
