@@ -129,6 +129,15 @@ int chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int n, int m, f
                     float* dist2, int32_t* idx1, int32_t* idx2, void* ws, size_t ws_bytes,
                     void* stream);
 
+/* chamfer_fwd_f32 with the loss reduction of every call site of the reference folded into the same
+ * launch (train.py:68-69,82-86: `torch.mean(dist1,1) + torch.mean(dist2,1)`; val.py:302-303):
+ *   loss (B) f32 = mean_j dist1[b,j] + mean_k dist2[b,k].  Per-warp partial sums are added with float
+ *   reductions, so the last bits of the loss depend on arrival order (dist/idx stay bit-exact).
+ *   Requires n, m >= 1.  Everything else as chamfer_fwd_f32.                                         */
+int chamfer_fwd_loss_f32(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
+                         float* dist2, int32_t* idx1, int32_t* idx2, float* loss, void* ws,
+                         size_t ws_bytes, void* stream);
+
 /* Replaces `chamfer_cuda_backward` = 2 x NmDistanceGradKernel (chamfer.cu:155-196).
  *   grad_xyz1 (B,n,3), grad_xyz2 (B,m,3): fully overwritten (the reference accumulates into
  *   caller-zeroed buffers with atomicAdd):

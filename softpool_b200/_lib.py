@@ -27,6 +27,7 @@ _SIGS = {
     "chamfer_fwd_f32": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, ctypes.c_size_t, _p]),
     "chamfer_bwd_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "chamfer_loss_f32": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "chamfer_fwd_loss_f32": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, ctypes.c_size_t, _p]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -216,6 +216,7 @@ chamfer_loss_kernel(const float* __restrict__ dist1, const float* __restrict__ d
         s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, d);
     }
     if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = s2; }
+    pdl_tail_trigger();
     __syncthreads();
     if (tid == 0) {
         float a = 0.f, c = 0.f;
@@ -239,26 +240,42 @@ extern "C" size_t chamfer_fwd_workspace_bytes(int B, int n, int m) {
     return spk::chamfer_tc_workspace_bytes(B, n, m);
 }
 
-extern "C" int chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int n, int m,
-                               float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* ws,
-                               size_t ws_bytes, void* stream) {
+static int chamfer_fwd_impl(const float* xyz1, const float* xyz2, int B, int n, int m,
+                            float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* loss, void* ws,
+                            size_t ws_bytes, void* stream, const char* who) {
     using namespace spk;
-    if (B < 0 || n < 0 || m < 0) return fail(SPK_E_BADARG, "chamfer_fwd_f32: negative size");
+    if (B < 0 || n < 0 || m < 0) return fail(SPK_E_BADARG, "%s: negative size", who);
+    if (loss != nullptr && (n < 1 || m < 1)) return fail(SPK_E_BADARG, "%s: the loss needs n, m >= 1", who);
     if (B == 0 || (n == 0 && m == 0)) return SPK_OK;
-    if ((n && (!dist1 || !idx1)) || (m && (!dist2 || !idx2))) return fail(SPK_E_BADARG, "chamfer_fwd_f32: null output");
+    if ((n && (!dist1 || !idx1)) || (m && (!dist2 || !idx2))) return fail(SPK_E_BADARG, "%s: null output", who);
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0 || m == 0) {   // reference leaves its zero-initialised outputs untouched
         if (n) { SPK_CUDA(cudaMemsetAsync(dist1, 0, (size_t)B * n * 4, st)); SPK_CUDA(cudaMemsetAsync(idx1, 0, (size_t)B * n * 4, st)); }
         if (m) { SPK_CUDA(cudaMemsetAsync(dist2, 0, (size_t)B * m * 4, st)); SPK_CUDA(cudaMemsetAsync(idx2, 0, (size_t)B * m * 4, st)); }
         return SPK_OK;
     }
-    if (!xyz1 || !xyz2) return fail(SPK_E_BADARG, "chamfer_fwd_f32: null input");
-    if (B > 65535) return fail(SPK_E_UNSUPPORTED, "chamfer_fwd_f32: B=%d > 65535", B);
-    if (use_tensor_path(n, m)) return chamfer_tc_forward(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, ws, ws_bytes, st);
+    if (!xyz1 || !xyz2) return fail(SPK_E_BADARG, "%s: null input", who);
+    if (B > 65535) return fail(SPK_E_UNSUPPORTED, "%s: B=%d > 65535", who, B);
+    if (use_tensor_path(n, m)) return chamfer_tc_forward(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, loss, ws, ws_bytes, st);
     const int per = CH_THREADS * CH_QPT;
     dim3 grid((max(n, m) + per - 1) / per, B, 2);
     SPK_CUDA(launch_k(chamfer_nn_exact_kernel, grid, dim3(CH_THREADS), 0, st, xyz1, xyz2, n, m, dist1, dist2, idx1, idx2));
+    if (loss != nullptr)      // small pair blocks: the loss is its own (tiny) launch
+        SPK_CUDA(launch_k(chamfer_loss_kernel, dim3(B), dim3(256), 0, st, (const float*)dist1, (const float*)dist2, n, m, loss));
     return SPK_OK;
+}
+
+extern "C" int chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int n, int m,
+                               float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* ws,
+                               size_t ws_bytes, void* stream) {
+    return chamfer_fwd_impl(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, nullptr, ws, ws_bytes, stream, "chamfer_fwd_f32");
+}
+
+extern "C" int chamfer_fwd_loss_f32(const float* xyz1, const float* xyz2, int B, int n, int m,
+                                    float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* loss,
+                                    void* ws, size_t ws_bytes, void* stream) {
+    if (!loss) return spk::fail(SPK_E_BADARG, "chamfer_fwd_loss_f32: null loss");
+    return chamfer_fwd_impl(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, loss, ws, ws_bytes, stream, "chamfer_fwd_loss_f32");
 }
 
 extern "C" int chamfer_bwd_f32(const float* xyz1, const float* xyz2, const float* g1, const float* g2,

@@ -120,6 +120,7 @@ struct PrepParams {
     ChamferMeta* meta;
     unsigned long long* packed1; unsigned long long* packed2;   // split jobs only: (dist bits << 32 | idx) minima, B*n / B*m
     int* counters; int n_counters;   // split jobs only: arrivals per (sample, direction, query tile)
+    float* loss;                     // fused loss only: (B) accumulators, zeroed here
 };
 
 __global__ void __launch_bounds__(256)
@@ -223,6 +224,8 @@ chamfer_prep_kernel(const PrepParams p) {
     }
     if (p.counters != nullptr && blockIdx.x == 0)
         for (int i = tid; i < p.n_counters; i += 256) p.counters[(size_t)b * p.n_counters + i] = 0;
+    if (p.loss != nullptr && blockIdx.x == 0 && tid == 0) p.loss[b] = 0.f;
+    pdl_tail_trigger();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -333,6 +336,7 @@ struct TcParams {
     int tiles1, tiles2;      // query tiles per sample in direction 0 / 1
     int S1, S2;              // target-range splits per query tile in direction 0 / 1 (1 = whole range in one job)
     unsigned long long* packed1; unsigned long long* packed2; int* counters;    // merge of split jobs
+    float* loss;             // fused loss (or NULL): (B) accumulators zeroed by the prep kernel
 };
 
 struct __align__(128) TcSmem {
@@ -352,6 +356,18 @@ __device__ __forceinline__ float min16(const float* v) {
     m0 = min3(m0, v[6], v[7]); m1 = min3(m1, v[8], v[9]);
     m0 = min3(m0, v[10], v[11]); m1 = min3(m1, v[12], v[13]);
     return min3(m0, m1, fminf(v[14], v[15]));
+}
+
+// ---- fused loss (train.py:68-69: mean(dist1,1) + mean(dist2,1)) -------------------------------------------------
+// Every exact warp adds its 32 rows' distances (shuffles), scales by 1/n or 1/m and adds the result to
+// loss[b] with ONE fire-and-forget float reduction (red.global.add.f32: no return value, nothing waits
+// for it).  (A deterministic variant -- partial sums parked per (tile, warp), an acq_rel ticket counter,
+// the last arrival summing in fixed order -- was measured 5 us slower at config A: the acquire holds the
+// next job's loads back.)
+__device__ __forceinline__ void loss_contribute(const TcParams& p, int b, int dir, int lane, float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if (lane == 0) atomicAdd(p.loss + b, v / (float)(dir ? p.m : p.n));
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -615,6 +631,8 @@ chamfer_tc_kernel(const TcParams p) {
                 if (lane == 0) mbar_arrive(&S.t4_empty[tb]);
                 TCLOG(" sb exact done", sb, 0);
             }
+            if (NS == 1 && p.loss != nullptr)
+                loss_contribute(p, b, dir, lane, live ? best_d : 0.f);
             if (live) {
                 if (NS == 1) {
                     ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = best_d;
@@ -639,12 +657,16 @@ chamfer_tc_kernel(const TcParams p) {
                     S.last = (old == NS - 1);
                 }
                 exact_bar();
+                float merged = 0.f;
                 if (S.last && live) {
                     unsigned long long v;
                     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"((dir ? p.packed2 : p.packed1) + (size_t)b * nq + gq) : "memory");
-                    ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = __uint_as_float((unsigned)(v >> 32));
+                    merged = __uint_as_float((unsigned)(v >> 32));
+                    ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = merged;
                     ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = (int)(unsigned)v;
                 }
+                if (S.last && p.loss != nullptr)                   // exactly one sub-job per query tile gets here
+                    loss_contribute(p, b, dir, lane, merged);
                 exact_bar();                                       // S.last is rewritten by the next split job
             }
         }
@@ -657,6 +679,7 @@ chamfer_tc_kernel(const TcParams p) {
     if (tid == 0 && blockIdx.x == 0) for (int i = 0; i < min(tlog_n, 320); ++i) printf("  t=%7lld %s %d %d\n", tlog_t[i], tlog_s[i], tlog_a[i], tlog_b[i]);
     if (tid == 0 && blockIdx.x < 2) printf("tc cta %d: chunks evaluated %d over %d (row, half, super-block) filters = %.3f each\n", blockIdx.x, S.dbg[0], S.dbg[1], (float)S.dbg[0] / (float)max(S.dbg[1], 1));
 #endif
+    pdl_tail_trigger();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -677,7 +700,7 @@ size_t chamfer_tc_workspace_bytes(int B, int n, int m) {
 }
 
 int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
-                       float* dist2, int32_t* idx1, int32_t* idx2, void* ws, size_t ws_bytes,
+                       float* dist2, int32_t* idx1, int32_t* idx2, float* loss, void* ws, size_t ws_bytes,
                        cudaStream_t st) {
     if (ws_bytes < chamfer_tc_workspace_bytes(B, n, m) || ws == nullptr)
         return fail(SPK_E_WORKSPACE, "chamfer_fwd_f32: workspace of %zu bytes needed, %zu given", chamfer_tc_workspace_bytes(B, n, m), ws_bytes);
@@ -721,6 +744,7 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
         pp.packed2 = pp.packed1 + (size_t)B * n;
         pp.counters = reinterpret_cast<int*>(pp.packed2 + (size_t)B * m);
     }
+    pp.loss = loss;
     const int slices = std::max(1, std::min(16, (n_pad + m_pad) / 512));
     SPK_CUDA(launch_k(chamfer_prep_kernel, dim3(slices, B), dim3(256), 0, st, pp));
 
@@ -730,6 +754,7 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
     tp.n = n; tp.m = m; tp.n_pad = n_pad; tp.m_pad = m_pad;
     tp.tiles1 = tiles1; tp.tiles2 = tiles2; tp.S1 = S1; tp.S2 = S2;
     tp.packed1 = pp.packed1; tp.packed2 = pp.packed2; tp.counters = pp.counters;
+    tp.loss = loss;
     // request enough shared memory that at most 2 CTAs share an SM (each owns 256 of the 512 TMEM columns)
     const size_t smem = std::max(sizeof(TcSmem) + 128, (size_t)80 * 1024);
     SPK_CUDA(cudaFuncSetAttribute(chamfer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -175,6 +175,7 @@ sp_gather_fwd_kernel(const GatherFwdParams p) {
             g_pref += r;
         }
     }
+    pdl_tail_trigger();
 }
 
 // Generic window max over an already written sp_cube (any k, cab): one thread per window.
@@ -378,6 +379,7 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
         }
         g = g_next;
     }
+    pdl_tail_trigger();
     if (p.bulk_out && tid == 0) bulk_wait<0>();
 }
 
@@ -621,6 +623,7 @@ sp_gather_bwd_pull_kernel(const GatherBwdPullParams p) {
         __syncthreads();                                           // the slot and the table are free again
         g += rows;
     }
+    pdl_tail_trigger();
 }
 
 }  // namespace spk

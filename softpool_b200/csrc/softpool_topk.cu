@@ -262,6 +262,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     TQ(4);
 
     // ---- emit ---------------------------------------------------------------------------------------------
+    pdl_tail_trigger();
     int32_t* orow = idx + (size_t)row * k;
     for (int j = tid; j < k; j += TOPK_THREADS) orow[j] = (int32_t)(0xFFFFFFFFu - (uint32_t)sel[j]);
     if (sp_idx != nullptr) {

@@ -34,8 +34,8 @@ int max_optin_smem();    // cudaDevAttrMaxSharedMemoryPerBlockOptin of the curre
 // tensor-core Chamfer forward (chamfer_tc.cu)
 size_t chamfer_tc_workspace_bytes(int B, int n, int m);
 int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
-                       float* dist2, int32_t* idx1, int32_t* idx2, void* ws, size_t ws_bytes,
-                       cudaStream_t st);
+                       float* dist2, int32_t* idx1, int32_t* idx2, float* loss /* or NULL */, void* ws,
+                       size_t ws_bytes, cudaStream_t st);
 
 bool pdl_enabled();      // SPK_NO_PDL=1 turns programmatic dependent launch off
 
@@ -143,6 +143,14 @@ __device__ __forceinline__ void pdl_trigger() {
 #endif
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Tail trigger: called by every thread once its main loop is done (only output stores / barrier teardown
+// left).  The next kernel's CTAs then launch while this kernel drains; their pdl_wait() still waits for
+// this kernel's completion and memory flush, so placement is a performance matter only.
+__device__ __forceinline__ void pdl_tail_trigger() {
+#ifndef SPK_NO_PDL_TAIL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 // (Early griddepcontrol.launch_dependents was measured twice on B200 and is NOT used: from every kernel the
 // step got slower, 107.7 vs 102.5 us -- waiting CTAs take resident slots from the persistent kernels; from
 // the short single-wave kernels only (top-k, Chamfer prep, loss) 94.9 vs 90.4 us -- the tensor-core kernel's

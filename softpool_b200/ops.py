@@ -147,8 +147,9 @@ def _chamfer_inputs(xyz1, xyz2):
     return xyz1.contiguous(), xyz2.contiguous()
 
 
-def chamfer_forward(xyz1, xyz2):
-    """-> dist1 (B,n) f32, dist2 (B,m) f32, idx1 (B,n) i32, idx2 (B,m) i32 (chamfer.cu:136-152)."""
+def chamfer_forward(xyz1, xyz2, want_loss=False):
+    """-> dist1 (B,n) f32, dist2 (B,m) f32, idx1 (B,n) i32, idx2 (B,m) i32 (chamfer.cu:136-152)
+    [, loss (B,) f32 = mean(dist1,1) + mean(dist2,1) from the same launch when want_loss]."""
     xyz1, xyz2 = _chamfer_inputs(xyz1, xyz2)
     B, n, _ = xyz1.shape
     m = xyz2.shape[1]
@@ -161,9 +162,42 @@ def chamfer_forward(xyz1, xyz2):
     ws_bytes = int(L.chamfer_fwd_workspace_bytes(B, n, m))
     ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
+        if want_loss:
+            loss = torch.empty((B,), dtype=torch.float32, device=dev)
+            check(L.chamfer_fwd_loss_f32(ptr(xyz1), ptr(xyz2), B, n, m, ptr(dist1), ptr(dist2), ptr(idx1),
+                                         ptr(idx2), ptr(loss), ptr(ws), ws_bytes, stream_of(xyz1)),
+                  "chamfer_fwd_loss_f32")
+            return dist1, dist2, idx1, idx2, loss
         check(L.chamfer_fwd_f32(ptr(xyz1), ptr(xyz2), B, n, m, ptr(dist1), ptr(dist2), ptr(idx1),
                                 ptr(idx2), ptr(ws), ws_bytes, stream_of(xyz1)), "chamfer_fwd_f32")
     return dist1, dist2, idx1, idx2
+
+
+class _ChamferMeanLoss(torch.autograd.Function):
+    """xyz1 (B,n,3), xyz2 (B,m,3) -> loss (B,) = mean(dist1,1) + mean(dist2,1): the expression at every
+    Chamfer call site of the reference (train.py:68-69,82-86), as ONE forward launch pair and one backward
+    launch (the 1/n, 1/m scaling of the upstream gradient is folded into the backward's inputs)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        dist1, dist2, idx1, idx2, loss = chamfer_forward(xyz1, xyz2, want_loss=True)
+        ctx.save_for_backward(xyz1.contiguous(), xyz2.contiguous(), idx1, idx2)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        B, n = idx1.shape
+        m = idx2.shape[1]
+        g = g_loss.contiguous().to(torch.float32)
+        g1 = (g / n)[:, None].expand(B, n).contiguous()
+        g2 = (g / m)[:, None].expand(B, m).contiguous()
+        return chamfer_backward(xyz1, xyz2, g1, g2, idx1, idx2)
+
+
+def chamfer_mean_loss(xyz1, xyz2):
+    """Differentiable per-sample Chamfer loss (B,), see _ChamferMeanLoss."""
+    return _ChamferMeanLoss.apply(xyz1, xyz2)
 
 
 def chamfer_backward(xyz1, xyz2, g1, g2, idx1, idx2):

@@ -293,3 +293,35 @@ def test_cluster_backward_matches_two_kernel_form(monkeypatch):
     rg1, rg2 = co.backward(a, b, g1, g2, i1.cpu().numpy(), i2.cpu().numpy())
     np.testing.assert_allclose(one[0].cpu().numpy(), rg1, rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(one[1].cpu().numpy(), rg2, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,n,m", [(32, 2048, 2048), (1, 4096, 16384), (3, 700, 1100), (2, 100, 90), (5, 2049, 1023)])
+def test_fused_loss_matches_mean_of_distances(B, n, m):
+    """chamfer_fwd_loss_f32: mean(dist1,1) + mean(dist2,1) from the forward launch itself (tensor path, split
+    jobs, and the small-shape path), dist/idx unchanged."""
+    from softpool_b200 import ops
+    a, b = clouds(B, n, m, seed=B + n)
+    t = lambda v: torch.from_numpy(v).to(dev())
+    d1, d2, i1, i2 = ops.chamfer_forward(t(a), t(b))
+    e1, e2, j1, j2, loss = ops.chamfer_forward(t(a), t(b), want_loss=True)
+    assert torch.equal(d1, e1) and torch.equal(d2, e2) and torch.equal(i1, j1) and torch.equal(i2, j2)
+    ref = d1.double().mean(1) + d2.double().mean(1)
+    torch.testing.assert_close(loss.double(), ref, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(loss, ops.chamfer_loss(d1, d2), rtol=1e-5, atol=1e-9)
+    for _ in range(3):                                        # the accumulator is re-zeroed by every call
+        torch.testing.assert_close(ops.chamfer_forward(t(a), t(b), want_loss=True)[4], loss, rtol=1e-5, atol=1e-9)
+
+
+def test_mean_loss_function_backward():
+    """ops.chamfer_mean_loss == mean(dist1,1)+mean(dist2,1) of chamferDist, forward and gradients."""
+    import softpool_b200 as spb
+    from softpool_b200 import ops
+    a, b = clouds(4, 1500, 2048, seed=21)
+    ta = torch.from_numpy(a).to(dev()).requires_grad_(True); tb = torch.from_numpy(b).to(dev()).requires_grad_(True)
+    w = torch.tensor([1.0, 0.5, 2.0, -1.0], device=dev())
+    (ops.chamfer_mean_loss(ta, tb) * w).sum().backward()
+    ua = torch.from_numpy(a).to(dev()).requires_grad_(True); ub = torch.from_numpy(b).to(dev()).requires_grad_(True)
+    d1, d2, _, _ = spb.chamferDist()(ua, ub)
+    ((d1.mean(1) + d2.mean(1)) * w).sum().backward()
+    torch.testing.assert_close(ta.grad, ua.grad, rtol=1e-4, atol=1e-8)
+    torch.testing.assert_close(tb.grad, ub.grad, rtol=1e-4, atol=1e-8)
