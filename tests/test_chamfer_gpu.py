@@ -325,3 +325,20 @@ def test_mean_loss_function_backward():
     ((d1.mean(1) + d2.mean(1)) * w).sum().backward()
     torch.testing.assert_close(ta.grad, ua.grad, rtol=1e-4, atol=1e-8)
     torch.testing.assert_close(tb.grad, ub.grad, rtol=1e-4, atol=1e-8)
+
+
+def test_real_clouds_from_the_reference_artefacts():
+    """Partial scans (2048 points, > 1200 exact duplicates each from resample_pcd) against their 16384-point ground
+    truths, and network outputs against ground-truth subsets: the reference's own PLY artefacts
+    (tests/golden/make_chamfer_real.py).  Bit-exact, batched and one cloud at a time (the val.py shape, B=1)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "chamfer_real.npz"))
+    o = cuda_forward(g["a"], g["b"])
+    for x, y in zip(o, (g["d1"], g["d2"], g["i1"], g["i2"])):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+    o = cuda_forward(g["c"], np.ascontiguousarray(g["b"][:, :4096]))
+    for x, y in zip(o, (g["e1"], g["e2"], g["j1"], g["j2"])):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+    for s in range(g["a"].shape[0]):
+        o = cuda_forward(g["a"][s:s + 1], g["b"][s:s + 1])
+        for x, y in zip(o, (g["d1"][s:s + 1], g["d2"][s:s + 1], g["i1"][s:s + 1], g["i2"][s:s + 1])):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32))

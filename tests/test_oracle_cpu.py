@@ -97,3 +97,24 @@ def test_chamfer_oracle_matches_reference_kernel_outputs(case):
     gx1, gx2 = co.backward(g["xyz1"], g["xyz2"], g["g1"], g["g2"], i1, i2)
     np.testing.assert_allclose(gx1, g["grad_xyz1"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(gx2, g["grad_xyz2"], rtol=1e-4, atol=1e-6)
+
+
+def test_real_cloud_fixture_is_what_the_oracle_computes():
+    """tests/golden/chamfer_real.npz (reference PLY artefacts): the stored answers are the C oracle's, and a plain
+    numpy brute force agrees on a slice (first-minimum rule on the many exact duplicates included)."""
+    import numpy as np
+    from oracle import chamfer_oracle as co
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chamfer_real.npz"))
+    a, b = g["a"][:1, :256], g["b"][:1, :4096]
+    d1, d2, i1, i2 = co.forward(np.ascontiguousarray(a), np.ascontiguousarray(b))
+    diff = b[0][None, :, :].astype(np.float64) - a[0][:, None, :].astype(np.float64)
+    dd = (diff * diff).sum(-1)
+    assert np.allclose(np.take_along_axis(dd, i1[0][:, None].astype(np.int64), 1)[:, 0], dd.min(1), rtol=1e-5, atol=1e-12)
+    assert np.allclose(d1[0], dd.min(1), rtol=1e-5, atol=1e-12)
+    # first minimum: no earlier target is (float32-)closer than the chosen one
+    chosen = np.take_along_axis(dd, i1[0][:, None].astype(np.int64), 1)
+    earlier = np.where(np.arange(dd.shape[1])[None, :] < i1[0][:, None], dd, np.inf)
+    assert (earlier.min(1) >= chosen[:, 0] * (1 - 1e-6)).all()
+    full = co.forward(g["a"], g["b"])
+    for x, y in zip(full, (g["d1"], g["d2"], g["i1"], g["i2"])):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
