@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SPK_ABI_VERSION 1
+#define SPK_ABI_VERSION 2   /* 2: + chamfer_fwd_loss_f32 */
 
 enum {
     SPK_OK = 0,
