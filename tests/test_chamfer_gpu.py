@@ -342,3 +342,35 @@ def test_real_clouds_from_the_reference_artefacts():
         o = cuda_forward(g["a"][s:s + 1], g["b"][s:s + 1])
         for x, y in zip(o, (g["d1"][s:s + 1], g["d2"][s:s + 1], g["i1"][s:s + 1], g["i2"][s:s + 1])):
             assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
+def test_tensor_path_randomized_stress(monkeypatch):
+    """Clustered, surface-like and near-degenerate clouds at several scales and offsets: the tensor path (fp16
+    accumulators, packed-minima filter, exact refinement) against the plain float32 kernel (SPK_CHAMFER_EXACT=1),
+    bit for bit.  This is the adversary of the filter's error model: many targets within 1e-7..1e-3 of the minimum."""
+    rng = np.random.default_rng(424242)
+    for trial in range(14):
+        B = int(rng.integers(1, 4)); n = int(rng.integers(300, 5000)); m = int(rng.integers(300, 6000))
+        kind = trial % 4
+        if kind == 0:      # points on a few planes + tiny normal noise
+            base = rng.random((B, n + m, 3), dtype=np.float32) - 0.5
+            base[..., 2] = np.round(base[..., 2] * 3) / 3 + rng.normal(0, 1e-6, (B, n + m)).astype(np.float32)
+        elif kind == 1:    # tight clusters
+            cent = rng.random((B, 12, 3), dtype=np.float32) - 0.5
+            pick = rng.integers(0, 12, (B, n + m))
+            base = np.take_along_axis(cent, pick[..., None].repeat(3, -1), 1) + rng.normal(0, 10.0 ** -int(rng.integers(3, 8)), (B, n + m, 3)).astype(np.float32)
+        elif kind == 2:    # a line (rank-1 geometry) with jitter
+            t = rng.random((B, n + m, 1), dtype=np.float32)
+            base = t * np.array([0.7, -0.2, 0.4], np.float32) + rng.normal(0, 1e-5, (B, n + m, 3)).astype(np.float32)
+        else:              # uniform with many exact duplicates
+            base = rng.random((B, n + m, 3), dtype=np.float32) - 0.5
+            base[:, ::3] = base[:, 1::3][:, : base[:, ::3].shape[1]]
+        scale = float(rng.choice([1.0, 1e-3, 250.0])); off = float(rng.choice([0.0, 17.0, -900.0]))
+        base = (base * scale + off).astype(np.float32)
+        a, b = np.ascontiguousarray(base[:, :n]), np.ascontiguousarray(base[:, n:])
+        monkeypatch.delenv("SPK_CHAMFER_EXACT", raising=False)
+        tc = cuda_forward(a, b)
+        monkeypatch.setenv("SPK_CHAMFER_EXACT", "1")
+        fma = cuda_forward(a, b)
+        for x, y in zip(tc, fma):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), "trial %d kind %d B=%d n=%d m=%d scale=%g off=%g" % (trial, kind, B, n, m, scale, off)
