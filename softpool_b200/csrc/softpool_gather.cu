@@ -9,11 +9,14 @@
 //     copy (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP), double-buffered, so the random
 //     index access hits shared memory, never HBM/L2, and every x byte is read exactly once; the
 //     sample's index list sits in shared memory as u16; outputs leave as 128-bit streaming stores;
-//   * backward: the upstream gradient tile arrives by bulk copy; one region per phase is scattered
-//     into a T x N shared-memory accumulator (points are unique inside a region: no conflicts, no
-//     atomics; ascending regions = fixed summation order); the T finished rows leave with one TMA
-//     bulk store (cp.async.bulk.global.shared::cta) while the next tile is accumulated in the other
-//     buffer.  grad_x is fully overwritten (zeros included): no memset.
+//   * backward (default, "pull"): per sample an inverse table (first slot of every point + links between the
+//     slots of one point) is built once in shared memory; the upstream gradient tile arrives by bulk copy;
+//     every thread sums the contributions of 4 consecutive points in registers (ascending regions = fixed
+//     summation order, no atomics) and writes them with one 128-bit streaming store per row.  grad_x is
+//     written exactly once (zeros included): no memset, no shared-memory accumulator;
+//   * backward ("push", for R*k >= 65535 or SPK_BWD=push): one region per phase is scattered into a T x N
+//     shared-memory accumulator (points are unique inside a region: no conflicts), the finished rows leave
+//     with one TMA bulk store (cp.async.bulk.global.shared::cta).  Bit-identical to the pull kernel.
 #include "spk_common.cuh"
 #include <stdlib.h>
 
