@@ -39,6 +39,10 @@ def test_library_is_sm100a_with_bulk_copies():
     assert "sm_100a" in elf
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass
+    # the Chamfer forward really runs on the 5th-gen tensor cores: tcgen05.mma, TMEM loads with 16-bit packing,
+    # and the packed 3-input 16-bit minimum (DPX) of its epilogue
+    for mnemonic in ("UTCHMMA", "LDTM.x16.PACK16BIT", "VIMNMX3.U16x2"):
+        assert mnemonic in sass, mnemonic
 
 
 def test_no_cpu_fallback():
