@@ -132,6 +132,26 @@ chamfer_prep_kernel(const PrepParams p) {
     const int b = blockIdx.y, tid = threadIdx.x;
     const float* P = p.xyz1 + (size_t)b * p.n * 3;
     const float* Q = p.xyz2 + (size_t)b * p.m * 3;
+    // this thread's own rows first (raw coordinates into registers): their trip to L2 / DRAM then overlaps the
+    // bounding-box pass instead of following it
+    constexpr int PRE = 2;
+    float prx[PRE], pry[PRE], prz[PRE];
+    {
+        const int total_rows = p.n_pad + p.m_pad;
+#pragma unroll
+        for (int j = 0; j < PRE; ++j) {
+            const int i = blockIdx.x * 256 + tid + j * (int)gridDim.x * 256;
+            prx[j] = pry[j] = prz[j] = 0.f;
+            if (i < total_rows) {
+                const bool first = i < p.n_pad;
+                const int r = first ? i : i - p.n_pad;
+                if (r < (first ? p.n : p.m)) {
+                    const float* sp = (first ? P : Q) + 3 * (size_t)r;
+                    prx[j] = __ldg(sp); pry[j] = __ldg(sp + 1); prz[j] = __ldg(sp + 2);
+                }
+            }
+        }
+    }
     // bounding box over both clouds (every CTA of the sample recomputes it: 12*(n+m) bytes from L2).
     // 128-bit loads, three per step = four whole points, so the axis of every lane is static.
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -206,7 +226,8 @@ chamfer_prep_kernel(const PrepParams p) {
     unsigned char* A1 = p.A1 + (size_t)b * p.n_pad * 32; unsigned char* B1 = p.B1 + (size_t)b * p.n_pad * 32;
     unsigned char* A2 = p.A2 + (size_t)b * p.m_pad * 32; unsigned char* B2 = p.B2 + (size_t)b * p.m_pad * 32;
     const int total = p.n_pad + p.m_pad;
-    for (int i = blockIdx.x * 256 + tid; i < total; i += gridDim.x * 256) {
+    int it_pre = 0;
+    for (int i = blockIdx.x * 256 + tid; i < total; i += gridDim.x * 256, ++it_pre) {
         const bool first = i < p.n_pad;
         const int r = first ? i : i - p.n_pad;
         const bool real = r < (first ? p.n : p.m);
@@ -214,7 +235,9 @@ chamfer_prep_kernel(const PrepParams p) {
         float4 raw = make_float4(INFINITY, INFINITY, INFINITY, 0.f);      // padding: infinitely far in the exact pass
         if (real) {
             const float* s = (first ? P : Q) + 3 * (size_t)r;
-            raw.x = __ldg(s); raw.y = __ldg(s + 1); raw.z = __ldg(s + 2);
+            if (it_pre == 0) { raw.x = prx[0]; raw.y = pry[0]; raw.z = prz[0]; }
+            else if (it_pre == 1) { raw.x = prx[1]; raw.y = pry[1]; raw.z = prz[1]; }
+            else { raw.x = __ldg(s); raw.y = __ldg(s + 1); raw.z = __ldg(s + 2); }
             ux = (raw.x - cx) * sc; uy = (raw.y - cy) * sc; uz = (raw.z - cz) * sc;
         }
         write_rows(first ? A1 : A2, first ? B1 : B2, r, real, ux, uy, uz, bias);

@@ -84,6 +84,18 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
 #define TQ(i)
 #endif
 
+    // ---- arg-max operands first: this thread's first point of the slice, up to 8 of the R rows, straight into
+    // registers -- issued BEFORE the row's own loads, so that both batches share one trip to L2 / DRAM instead
+    // of queueing behind each other (the arg-max itself is formed after the keys are parked)
+    constexpr int AM_PRE = 8;
+    float am[AM_PRE];
+    const int am_slice = (N + R - 1) / R;
+    const int am_s0 = r * am_slice, am_s1 = min(N, am_s0 + am_slice);
+    const float* kb = keys + (size_t)b * R * N;
+    const bool am_mine = id_activa != nullptr && am_s0 + tid < am_s1;
+#pragma unroll
+    for (int rr = 0; rr < AM_PRE; ++rr) am[rr] = (am_mine && rr < R) ? __ldg(kb + (size_t)rr * N + am_s0 + tid) : 0.f;
+
     // ---- 1. load: thread t owns the E consecutive points n = t*E .. t*E+E-1 ------------------------
     // (all loads are issued before the first use: order_key is branch-free, nothing serialises them)
     const int n0 = tid * E;
@@ -123,10 +135,24 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
 
     // ---- argmax over the R rows for this CTA's slice of n (softpool.py:95) --------------------------
     if (id_activa != nullptr) {
-        const int slice = (N + R - 1) / R;
-        const int s0 = r * slice, s1 = min(N, s0 + slice);
-        const float* kb = keys + (size_t)b * R * N;
-        for (int n = s0 + tid; n < s1; n += TOPK_THREADS) {
+        const int s0 = am_s0, s1 = am_s1;
+        if (am_mine) {                                           // first point: the first AM_PRE rows are in registers
+            uint32_t bestk = order_key(am[0]);
+            int besti = 0;
+#pragma unroll
+            for (int rr = 1; rr < AM_PRE; ++rr) {
+                const uint32_t kk = order_key(am[rr]);
+                const bool better = rr < R && kk > bestk;        // strict: first maximum / first NaN
+                bestk = better ? kk : bestk; besti = better ? rr : besti;
+            }
+            for (int rr = AM_PRE; rr < R; ++rr) {
+                const uint32_t kk = order_key(__ldg(kb + (size_t)rr * N + s0 + tid));
+                const bool better = kk > bestk;
+                bestk = better ? kk : bestk; besti = better ? rr : besti;
+            }
+            id_activa[(size_t)b * N + s0 + tid] = (int64_t)besti;
+        }
+        for (int n = s0 + tid + TOPK_THREADS; n < s1; n += TOPK_THREADS) {
             uint32_t bestk = order_key(__ldg(kb + n));
             int besti = 0;
 #pragma unroll 8
