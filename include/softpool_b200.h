@@ -138,7 +138,8 @@ int chamfer_fwd_loss_f32(const float* xyz1, const float* xyz2, int B, int n, int
                          float* dist2, int32_t* idx1, int32_t* idx2, float* loss, void* ws,
                          size_t ws_bytes, void* stream);
 
-/* Replaces `chamfer_cuda_backward` = 2 x NmDistanceGradKernel (chamfer.cu:155-196).
+/* Replaces `chamfer_cuda_backward` = 2 x NmDistanceGradKernel (chamfer.cu:155-196); one launch
+ * (a thread-block cluster per sample: direct terms, cluster barrier, scatter terms).
  *   grad_xyz1 (B,n,3), grad_xyz2 (B,m,3): fully overwritten (the reference accumulates into
  *   caller-zeroed buffers with atomicAdd):
  *     grad_xyz1[j]      = 2 g1[j] (p_j - q_idx1[j])  -  sum_{k: idx2[k]==j} 2 g2[k] (q_k - p_j)

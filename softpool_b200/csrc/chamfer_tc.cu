@@ -5,24 +5,33 @@
 //
 // Idea.  The pairwise block IS a dense contraction:  d(p,q) = |p|^2 + |q|^2 - 2 p.q.  With fp16
 // hi/lo splits of the (centred, power-of-two scaled) coordinates and 3-way fp16 splits of the
-// norms, ONE K=16 MMA row pair produces the squared distance in fp32 with absolute error
-// e <= ~2^-17 (scaled units):
-//     A'(p) = [-2xh,-2xh,-2xl, -2yh,-2yh,-2yl, -2zh,-2zh,-2zl,  nh,nm,nl,  1,1,1,  0]
-//     B'(q) = [  xh,  xl,  xh,   yh,  yl,  yh,   zh,  zl,  zh,   1, 1, 1,  mh,mm,ml, 0]
-// The approximate block only FILTERS: per query row the epilogue keeps the minimum of every
-// 16-target chunk (one 3-input FMNMX3 per two elements -- the whole per-element cost), then only
-// chunks whose minimum is within tau = 2e of the row minimum are re-evaluated with the reference's
-// exact float32 expression  d = fma(dz,dz, fma(dx,dx, dy*dy))  and first-minimum tie rule.  A chunk
-// that holds the true nearest neighbour always passes the filter (its approximate distance is
-// <= d_true + e <= d_any + e <= approx_any + 2e), so the result equals the brute-force one.
+// norms, ONE K=16 MMA row pair produces bias + the squared distance with absolute error
+// e <= ~2^-17 (scaled units) before the accumulator's own rounding:
+//     A'(p) = [-2xh,-2xh,-2xl, -2yh,-2yh,-2yl, -2zh,-2zh,-2zl,  nh,nm,nl,  1,1,1,  1   ]
+//     B'(q) = [  xh,  xl,  xh,   yh,  yl,  yh,   zh,  zl,  zh,   1, 1, 1,  mh,mm,ml, bias]
+// The accumulator is fp16 (one instruction forms the whole sum, so its only fp16 rounding is the last
+// one) and bias (a power of two above the error bound) keeps every value a POSITIVE fp16, whose bit
+// pattern orders like its value: the epilogue reads two columns per register (tcgen05.ld ...pack::16b)
+// and reduces with VIMNMX3.U16x2, four new elements per instruction (tools/micro/minbench.cu: twice the
+// element rate of any fp32 min).  Target rows are permuted inside groups of 32 (b_row_of) so that the two
+// 16-bit lanes of a packed minimum are two contiguous chunks of 16 targets.
+// The approximate block only FILTERS: per query row the minimum of every 16-target chunk is kept, then only
+// chunks whose minimum is within the slack (relative 2^-8 for the fp16 rounding, absolute tau = 2e) of the
+// row minimum -- or of the exact best so far -- are re-evaluated with the reference's exact float32
+// expression  d = fma(dz,dz, fma(dx,dx, dy*dy))  and first-minimum tie rule.  A chunk that holds the true
+// nearest neighbour always passes the filter (its approximate distance is <= d_true + e <= d_any + e <=
+// approx_any + 2e), so the result equals the brute-force one.
 //
-// Kernel structure (persistent, 2 CTAs per SM; a job = 128 queries of one sample and direction):
-//   warp 0   TMA producer: A tile (128 x 32 B) per job, B tiles (128 targets x 32 B) through a ring,
-//            and the raw float4 coordinates of every 1024-target super-block (for the exact pass)
-//   warp 1   TMEM alloc (256 columns = 2 accumulator buffers of 128) + single-thread tcgen05.mma
-//            issue (M=128, N=128, K=16, kind::f16, fp32 accumulate) + tcgen05.commit -> mbarriers
-//   warps 2-9  epilogue: tcgen05.ld 32x32b.x32 -> minima of 16-target chunks in registers; every
-//            1024 targets the filter + exact re-evaluation from shared memory; final store
+// Kernel structure (persistent, 2 CTAs per SM; a job = 128 queries of one sample and direction, or -- when
+// the grid would be underfilled -- a sub-range of that job's targets, merged through a 64-bit atomicMin):
+//   warp 0     TMA producer: A tile (128 x 32 B) per job (double-buffered), B tiles (128 targets x 32 B) through
+//              a ring, and the raw float4 coordinates of every 1024-target super-block (for the exact pass)
+//   warp 1     TMEM alloc (256 columns = 2 accumulator buffers of 128) + single-thread tcgen05.mma issue
+//              (M=128, N=128, K=16, kind::f16, fp16 accumulate) + tcgen05.commit -> mbarriers
+//   warps 2-5  "min" warps, one per TMEM lane quarter: accumulator -> registers (buffer handed back at once)
+//              -> packed chunk minima -> shared memory, double-buffered per super-block
+//   warps 6-9  "exact" warps, one thread per query row: filter, exact re-evaluation from shared memory,
+//              running best, final store (+ the fused mean loss); up to two super-blocks behind the min warps
 // Operands are pre-formatted by chamfer_prep_kernel in the canonical no-swizzle K-major layout
 // (8-row x 16-byte core matrices, LBO = 128 B, SBO = 256 B), so tiles move with 1-D bulk copies.
 #include "spk_common.cuh"
