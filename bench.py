@@ -10,8 +10,11 @@ One STEP = one pass of the hot path over one batch of B synthetic clouds (per GP
 `value` = whole-job Mpoints/s = (n_gpus * B * N points) / (max-over-ranks step time), inputs
 resident in HBM, the step replayed as a CUDA graph, inputs rotating over several buffer sets whose
 footprint exceeds the 126 MB L2.  `e2e` = same step through the public Python API with HOST
-(pinned) inputs, H2D/D2H copies inside the timed region.  `roofline` = dominant kernel, timed live
-with CUDA events in an instrumented pass (L2 flushed before every step).  `cpu_baseline` = the CPU
+(pinned) inputs, H2D/D2H copies inside the timed region (step i+1's H2D runs on a copy stream under step
+i's kernels).  `roofline` = dominant call, timed live with CUDA events around CUDA-graph replays of that call
+alone over the rotating buffer sets (its inputs are never L2-resident); `roofline_softpool` / `roofline_chamfer`
+carry both groups.  `chains_overlapped` (informational) = the same step with the SoftPool chain and the Chamfer
+chain as two branches of one graph.  `cpu_baseline` = the CPU
 port of the reference path (oracle/softpool_torch_port.py + oracle/chamfer_oracle.c) on this host.
 Prints ONE JSON line on rank 0.
 """
