@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsoftpool_b200.so")
-SOURCES = ["capi.cu", "softpool_topk.cu", "softpool_gather.cu", "chamfer.cu", "chamfer_tc.cu"]
+SOURCES = ["capi.cu", "softpool_topk.cu", "softpool_gather.cu", "chamfer.cu", "chamfer_dense.cu", "chamfer_tc.cu"]
 HEADERS = [os.path.join(CSRC, "spk_common.cuh"),
            os.path.join(HERE, os.pardir, "include", "softpool_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

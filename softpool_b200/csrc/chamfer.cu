@@ -227,17 +227,32 @@ chamfer_loss_kernel(const float* __restrict__ dist1, const float* __restrict__ d
 
 }  // namespace spk
 
-// Pair blocks below this size are not worth the prep pass + tensor pipeline set-up.
-static bool use_tensor_path(int n, int m) {
-    if (n < 1 || m < 1) return false;
-    const char* e = getenv("SPK_CHAMFER_EXACT");           // debugging / A-B switch: force the FMA path
-    if (e && e[0] == '1') return false;
-    return (long long)n * m >= 256LL * 256LL;
+// Forward paths (all bit-identical; tests/test_chamfer_gpu.py runs every shape through each of them):
+//   0  plain float32 FMA kernel           pair blocks below 256 x 256, clouds above the sorted path's limit
+//   1  dense tensor-core kernel           every pair on the tensor pipe (chamfer_dense.cu): small and medium pair blocks
+//   2  sorted search + tensor-core filter ~100 exact distances per query whatever m is (chamfer_tc.cu): large clouds
+// Measured crossover on a B200 (tools/time_chamfer.py): 32 x 2048 x 2048 dense 24 us / sorted 36 us, 32 x 8192 x 8192
+// dense 251 us / sorted 164 us.  SPK_CHAMFER_PATH=exact|dense|sorted forces one (A/B and tests).
+static int chamfer_path(int B, int n, int m) {
+    if (n < 1 || m < 1) return 0;
+    const char* e = getenv("SPK_CHAMFER_PATH");
+    if (e && e[0] == 'e') return 0;
+    const char* e2 = getenv("SPK_CHAMFER_EXACT");           // (round-1 name of the same switch)
+    if (e2 && e2[0] == '1') return 0;
+    if ((long long)n * m < 256LL * 256LL) return 0;
+    const bool sorted_ok = spk::chamfer_tc_supported(n, m);
+    if (e && e[0] == 'd') return 1;
+    if (e && e[0] == 's') return sorted_ok ? 2 : 1;
+    // the dense kernel's time grows with B n m, the sorted search's with B (n + m): large pair blocks go to the search
+    if (sorted_ok && (long long)n * m >= 4096LL * 4096LL && (long long)B * (n + m) >= 65536) return 2;
+    return 1;
 }
 
 extern "C" size_t chamfer_fwd_workspace_bytes(int B, int n, int m) {
     if (B < 1 || n < 1 || m < 1) return 0;
-    return spk::chamfer_tc_workspace_bytes(B, n, m);
+    size_t w = spk::chamfer_dense_workspace_bytes(B, n, m);
+    if (spk::chamfer_tc_supported(n, m)) w = std::max(w, spk::chamfer_tc_workspace_bytes(B, n, m));
+    return w;
 }
 
 static int chamfer_fwd_impl(const float* xyz1, const float* xyz2, int B, int n, int m,
@@ -256,7 +271,9 @@ static int chamfer_fwd_impl(const float* xyz1, const float* xyz2, int B, int n, 
     }
     if (!xyz1 || !xyz2) return fail(SPK_E_BADARG, "%s: null input", who);
     if (B > 65535) return fail(SPK_E_UNSUPPORTED, "%s: B=%d > 65535", who, B);
-    if (use_tensor_path(n, m)) return chamfer_tc_forward(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, loss, ws, ws_bytes, st);
+    const int path = chamfer_path(B, n, m);
+    if (path == 2) return chamfer_tc_forward(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, loss, ws, ws_bytes, st);
+    if (path == 1) return chamfer_dense_forward(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, loss, ws, ws_bytes, st);
     const int per = CH_THREADS * CH_QPT;
     dim3 grid((max(n, m) + per - 1) / per, B, 2);
     SPK_CUDA(launch_k(chamfer_nn_exact_kernel, grid, dim3(CH_THREADS), 0, st, xyz1, xyz2, n, m, dist1, dist2, idx1, idx2));

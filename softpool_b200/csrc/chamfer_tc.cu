@@ -1,77 +1,63 @@
-// chamfer_tc.cu -- Chamfer forward on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+// chamfer_tc.cu -- Chamfer forward: cell-sorted clouds, a tcgen05 chunk filter, exact fp32 refinement (sm_100a).
 //
-// Replaces NmDistanceKernel x2 (reference distance/chamfer/chamfer.cu:12-143) and returns
-// bit-identical dist/idx for finite inputs, yet evaluates the n x m pair block on the tensor pipe.
+// Replaces NmDistanceKernel x2 (reference distance/chamfer/chamfer.cu:12-143) and returns bit-identical
+// dist/idx (same float32 expression, first-minimum rule; non-finite samples follow the reference's 512-target
+// batching statement for statement), without evaluating the n x m pair block.
 //
-// Idea.  The pairwise block IS a dense contraction:  d(p,q) = |p|^2 + |q|^2 - 2 p.q.  With fp16
-// hi/lo splits of the (centred, power-of-two scaled) coordinates and 3-way fp16 splits of the
-// norms, ONE K=16 MMA row pair produces bias + the squared distance with absolute error
-// e <= ~2^-17 (scaled units) before the accumulator's own rounding:
-//     A'(p) = [-2xh,-2xh,-2xl, -2yh,-2yh,-2yl, -2zh,-2zh,-2zl,  nh,nm,nl,  1,1,1,  1   ]
-//     B'(q) = [  xh,  xl,  xh,   yh,  yl,  yh,   zh,  zl,  zh,   1, 1, 1,  mh,mm,ml, bias]
-// The accumulator is fp16 (one instruction forms the whole sum, so its only fp16 rounding is the last
-// one) and bias (a power of two above the error bound) keeps every value a POSITIVE fp16, whose bit
-// pattern orders like its value: the epilogue reads two columns per register (tcgen05.ld ...pack::16b)
-// and reduces with VIMNMX3.U16x2, four new elements per instruction (tools/micro/minbench.cu: twice the
-// element rate of any fp32 min).  Target rows are permuted inside groups of 32 (b_row_of) so that the two
-// 16-bit lanes of a packed minimum are two contiguous chunks of 16 targets.
-// The approximate block only FILTERS: per query row the minimum of every 16-target chunk is kept, then only
-// chunks whose minimum is within the slack (relative 2^-8 for the fp16 rounding, absolute tau = 2e) of the
-// row minimum -- or of the exact best so far -- are re-evaluated with the reference's exact float32
-// expression  d = fma(dz,dz, fma(dx,dx, dy*dy))  and first-minimum tie rule.  A chunk that holds the true
-// nearest neighbour always passes the filter (its approximate distance is <= d_true + e <= d_any + e <=
-// approx_any + 2e), so the result equals the brute-force one.
-//
-// Kernel structure (persistent, 2 CTAs per SM; a job = 128 queries of one sample and direction, or -- when
-// the grid would be underfilled -- a sub-range of that job's targets, merged through a 64-bit atomicMin):
-//   warp 0     TMA producer: A tile (128 x 32 B) per job (double-buffered), B tiles (128 targets x 32 B) through
-//              a ring, and the raw float4 coordinates of every 1024-target super-block (for the exact pass)
-//   warp 1     TMEM alloc (256 columns = 2 accumulator buffers of 128) + single-thread tcgen05.mma issue
-//              (M=128, N=128, K=16, kind::f16, fp16 accumulate) + tcgen05.commit -> mbarriers
-//   warps 2-5  "min" warps, one per TMEM lane quarter: accumulator -> registers (buffer handed back at once)
-//              -> packed chunk minima -> shared memory, double-buffered per super-block
-//   warps 6-9  "exact" warps, one thread per query row: filter, exact re-evaluation from shared memory,
-//              running best, final store (+ the fused mean loss); up to two super-blocks behind the min warps
-// Operands are pre-formatted by chamfer_prep_kernel in the canonical no-swizzle K-major layout
-// (8-row x 16-byte core matrices, LBO = 128 B, SBO = 256 B), so tiles move with 1-D bulk copies.
+// Round 1 evaluated every pair on the tensor pipe and was bound by TMEM: an accumulator column is occupied for
+// the whole MMA -> commit -> tcgen05.ld -> release round trip (~600 cycles, tools/micro/tc_pipe2_bench.cu), so
+// 512 columns x 128 lanes cap an SM at ~110 pair distances per cycle whatever the kernel does.  This version
+// spends the tensor pipe on 16x fewer outputs:
+//   prep   chamfer_sort_kernel: one CTA per (sample, cloud).  Counting sort of the points by Hilbert cell
+//          (16^3 grid on the cloud's bounding box), so that CHUNK = 16 consecutive points are neighbours.  Per
+//          chunk: bounding box, centre c, radius r.  Emits the sorted points (x, y, z, original index), fp16
+//          operand rows A'(p) for every point as a QUERY and B'(c) for every CHUNK CENTRE as a target.
+//   search chamfer_search_kernel: a job = 128 queries of one sample and direction; per pass of 128 chunks
+//          (2048 targets) ONE M=128 x N=128 x K=16 tcgen05.mma gives, for every query, 128 values
+//              V_j = bias + |p - c_j|^2 - 1.5 r_j^2      (scaled units, fp16 accumulators)
+//          A chunk can only hold a point nearer than the best so far if |p - c_j| <= sqrt(best) + r_j, and
+//          (s + r)^2 <= 3 s^2 + 1.5 r^2 (AM-GM), so "V_j <= bias + 3 best" is a NECESSARY condition -- one
+//          packed 16-bit compare per chunk (3 integer instructions per two chunks).  Survivors are tested against
+//          the chunk's bounding box in float32, and only then are the chunk's 16 points evaluated with the
+//          reference's exact expression  d = fma(dz,dz, fma(dx,dx, dy*dy))  and first-minimum tie rule on the
+//          ORIGINAL indices.  Every approximation errs on the side of evaluating more (slack: relative 2^-8 for the
+//          fp16 accumulator, absolute tau for the fp16 operand splits), so the result equals brute force.
+// ~100 exact distances per query instead of m (tools/chunk_search_estimate.py), independent of m for uniform data.
 #include "spk_common.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
-#ifndef SPK_SPIN
-#define SPK_SPIN 0
-#endif
-
 namespace spk {
 
-constexpr int TC_TILE = 128;            // queries per CTA = targets per shared-memory B tile
-#ifndef SPK_TC_N
-#define SPK_TC_N 128
-#endif
-constexpr int TC_N = SPK_TC_N;          // targets per MMA (accumulator buffer width, TMEM columns)
-constexpr int TC_NBUF = 256 / TC_N;              // accumulator buffers: hides the release -> MMA -> commit round trip
-constexpr int TC_STAGES = 4;            // B-tile ring depth
-constexpr int TC_THREADS = 320;         // 10 warps
-constexpr int TC_SB_TILES = 8;          // tiles per super-block (1024 targets)
-constexpr int TC_SB_TARGETS = TC_SB_TILES * TC_TILE;
-constexpr int TC_CHUNK = 16;            // targets per filter chunk
-constexpr int TC_CM_WORDS = TC_SB_TARGETS / 32;   // packed words (2 chunk minima each) per query row and super-block
-constexpr int TC_MIN_WARPS = 4, TC_EXACT_WARPS = 4;
-constexpr int TC_T4_BUFS = 2;           // raw-coordinate buffers: the exact warps lag the operand stream by up to two super-blocks
+constexpr int TC_TILE = 128;             // queries per job = TMEM lanes
+constexpr int TC_CHUNK = 16;             // targets per chunk
+constexpr int TC_NC = 128;               // chunks per pass = accumulator columns of one MMA
+constexpr int TC_THREADS = 128;          // search kernel: one thread per query row
 constexpr int TC_TILE_BYTES = TC_TILE * 32;
-constexpr float TC_PAD_NORM = 30000.f;  // norm of padding targets: never the minimum
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_BITS = 4;             // Morton grid: 2^SORT_BITS cells per axis
+constexpr int SORT_CELLS = 1 << (3 * SORT_BITS);
+constexpr int TC_MAX_POINTS = 32768;     // per cloud: the sort keeps 6 bytes per point in shared memory
+constexpr float TC_PAD_NORM = 30000.f;   // norm term of padding chunks: never pass the filter
+constexpr float TC_RCAP_MAX = 1.f;        // largest 1.5 r^2 term folded into a chunk's operand (scaled units); the cap adapts per cloud
 
-struct ChamferMeta {                    // per sample, written by the prep kernel
-    float cx, cy, cz;                   // centre (bounding-box midpoint of both clouds)
-    float scale;                        // power of two: |(x - c) * scale| <= 1
-    float tau;                          // filter slack in scaled squared units
-    float scale2;                       // scale * scale
-    float bias;                         // power of two added to every approximate distance (keeps them > 0)
-    float nonfinite;                    // != 0: some coordinate is NaN/inf -> every chunk is evaluated exactly
+struct ChamferMeta {                     // per sample, written by the sort kernel
+    float cx, cy, cz;                    // centre (bounding-box midpoint of both clouds)
+    float scale;                         // power of two: |(x - c) * scale| <= 1
+    float tau;                           // filter slack in scaled squared units
+    float scale2;                        // scale * scale
+    float bias;                          // (unused: the bias is per target cloud, ChamferGrid)
+    float nonfinite;                     // != 0: NaN/inf coordinate or hopeless conditioning -> reference-order brute force
+};
+
+struct ChamferGrid {                     // per (sample, cloud): the Morton grid the cloud was sorted on
+    float lo[3], inv[3];                 // cell = clamp((x - lo) * inv, 0, 2^SORT_BITS - 1) per axis
+    float bias;                          // power of two added to every V of this cloud's chunks (keeps them positive fp16)
+    float pad;
 };
 
 // ---------------------------------------------------------------------------------------------
-// prep: centre/scale per sample, fp16 split operands in UMMA canonical layout
+// operand formatting
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split2(float v, __half& h, __half& l) {
     h = __float2half_rn(v);
@@ -83,180 +69,342 @@ __device__ __forceinline__ void split3(float v, __half& h, __half& m, __half& l)
     m = __float2half_rn(r1);
     l = __float2half_rn(r1 - __half2float(m));
 }
-
-// byte offset of row r's first 16-byte K-chunk inside an operand array
+// byte offset of row r's first 16-byte K-chunk inside an operand array (UMMA canonical no-swizzle K-major layout:
+// 8-row x 16-byte core matrices, 128 B between the two K chunks, 256 B between 8-row groups)
 __device__ __forceinline__ size_t op_row_offset(int r) { return (size_t)(r >> 3) * 256 + (size_t)(r & 7) * 16; }
-
-// B rows are permuted inside every aligned group of 32 targets: target u of the group sits in row
-// ((u & 15) << 1) | (u >> 4), so that the EVEN accumulator columns of the group are targets 0..15 and the
-// ODD columns targets 16..31 -- the two 16-bit lanes of the packed minimum then hold two contiguous chunks.
+// Target rows are permuted inside every aligned group of 32: chunk u of the group sits in row
+// ((u & 15) << 1) | (u >> 4), so that the EVEN accumulator columns of the group are chunks 0..15 and the ODD
+// columns chunks 16..31 -- bit i / 16+i of a packed-compare mask then IS chunk i / 16+i.
 __device__ __forceinline__ int b_row_of(int r) { return (r & ~31) | ((r & 15) << 1) | ((r >> 4) & 1); }
 
-__device__ __forceinline__ void write_rows(unsigned char* opA, unsigned char* opB, int r, bool real,
-                                           float ux, float uy, float uz, float bias) {
+//  A'(p) = [-2xh,-2xh,-2xl, -2yh,-2yh,-2yl, -2zh,-2zh,-2zl,  nh,nm,nl,  1,1,1,  1   ]     n = |p|^2
+//  B'(c) = [  xh,  xl,  xh,   yh,  yl,  yh,   zh,  zl,  zh,   1, 1, 1,  mh,mm,ml, bias]    m = |c|^2 - sub
+__device__ __forceinline__ void write_a_row(unsigned char* opA, int r, bool real, float ux, float uy, float uz) {
     __align__(16) __half a[16];
-    __align__(16) __half b[16];
     if (real) {
         __half xh, xl, yh, yl, zh, zl, nh, nm, nl;
         split2(ux, xh, xl); split2(uy, yh, yl); split2(uz, zh, zl);
-        const float nrm = fmaf(uz, uz, fmaf(uy, uy, ux * ux));
-        split3(nrm, nh, nm, nl);
-        const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f), m2 = __float2half_rn(-2.f);
+        split3(fmaf(uz, uz, fmaf(uy, uy, ux * ux)), nh, nm, nl);
+        const __half one = __float2half_rn(1.f), m2 = __float2half_rn(-2.f);
         a[0] = __hmul(m2, xh); a[1] = a[0]; a[2] = __hmul(m2, xl);
         a[3] = __hmul(m2, yh); a[4] = a[3]; a[5] = __hmul(m2, yl);
         a[6] = __hmul(m2, zh); a[7] = a[6]; a[8] = __hmul(m2, zl);
         a[9] = nh; a[10] = nm; a[11] = nl; a[12] = one; a[13] = one; a[14] = one; a[15] = one;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = __float2half_rn(0.f);
+    }
+    const size_t o = op_row_offset(r);
+    *reinterpret_cast<uint4*>(opA + o) = *reinterpret_cast<const uint4*>(&a[0]);
+    *reinterpret_cast<uint4*>(opA + o + 128) = *reinterpret_cast<const uint4*>(&a[8]);
+}
+__device__ __forceinline__ void write_b_row(unsigned char* opB, int chunk, bool real, float ux, float uy, float uz, float sub, float bias) {
+    __align__(16) __half b[16];
+    const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
+    if (real) {
+        __half xh, xl, yh, yl, zh, zl, nh, nm, nl;
+        split2(ux, xh, xl); split2(uy, yh, yl); split2(uz, zh, zl);
+        split3(fmaf(uz, uz, fmaf(uy, uy, ux * ux)) - sub, nh, nm, nl);
         b[0] = xh; b[1] = xl; b[2] = xh; b[3] = yh; b[4] = yl; b[5] = yh; b[6] = zh; b[7] = zl; b[8] = zh;
         b[9] = one; b[10] = one; b[11] = one; b[12] = nh; b[13] = nm; b[14] = nl; b[15] = __float2half_rn(bias);
     } else {
-        const __half zero = __float2half_rn(0.f), one = __float2half_rn(1.f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { a[i] = zero; b[i] = zero; }
-        b[9] = one; b[12] = __float2half_rn(TC_PAD_NORM);     // a padding target is "infinitely" far
+        for (int i = 0; i < 16; ++i) b[i] = zero;
+        b[9] = one; b[12] = __float2half_rn(TC_PAD_NORM);          // a padding chunk is "infinitely" far
     }
-    const size_t o = op_row_offset(r), ob = op_row_offset(b_row_of(r));
-    *reinterpret_cast<uint4*>(opA + o) = *reinterpret_cast<const uint4*>(&a[0]);
-    *reinterpret_cast<uint4*>(opA + o + 128) = *reinterpret_cast<const uint4*>(&a[8]);
-    *reinterpret_cast<uint4*>(opB + ob) = *reinterpret_cast<const uint4*>(&b[0]);
-    *reinterpret_cast<uint4*>(opB + ob + 128) = *reinterpret_cast<const uint4*>(&b[8]);
+    const size_t o = op_row_offset(b_row_of(chunk));
+    *reinterpret_cast<uint4*>(opB + o) = *reinterpret_cast<const uint4*>(&b[0]);
+    *reinterpret_cast<uint4*>(opB + o + 128) = *reinterpret_cast<const uint4*>(&b[8]);
 }
 
-struct PrepParams {
-    const float* xyz1; const float* xyz2;
-    int n, m, n_pad, m_pad;
-    unsigned char* A1; unsigned char* B1; unsigned char* A2; unsigned char* B2;   // per sample n_pad*32 / m_pad*32 bytes
-    float4* T1; float4* T2;          // raw coordinates (x,y,z,0), padded per sample to n_pad / m_pad rows
+// ---------------------------------------------------------------------------------------------
+// prep: bounding boxes, Morton-cell counting sort, sorted points, operand rows, chunk boxes
+// ---------------------------------------------------------------------------------------------
+struct SortParams {
+    const float* xyz[2];                 // (B, n[c], 3)
+    int n[2], n_pad[2], nc[2], nc_pad[2];
+    float4* S[2];                        // sorted points (x, y, z, original index bits), nc_pad * 16 per sample
+    unsigned char* A[2];                 // query operand rows, n_pad * 32 bytes per sample
+    unsigned char* Bc[2];                // chunk-centre operand rows, nc_pad * 32 bytes per sample
+    float4* box[2];                      // per chunk {lo.xyz, capped flag}, {hi.xyz, 0}; nc_pad * 2 per sample
+    uint16_t* cellstart[2];              // first sorted position of every Morton cell, SORT_CELLS per sample
+    ChamferGrid* grid[2];                // per sample
     ChamferMeta* meta;
-    unsigned long long* packed1; unsigned long long* packed2;   // split jobs only: (dist bits << 32 | idx) minima, B*n / B*m
-    int* counters; int n_counters;   // split jobs only: arrivals per (sample, direction, query tile)
-    float* loss;                     // fused loss only: (B) accumulators, zeroed here
+    float* loss;                         // fused loss only: (B) accumulators, zeroed here
+    int stage;                           // the clouds' raw coordinates fit in shared memory next to the sort arrays
 };
 
-__global__ void __launch_bounds__(256)
-chamfer_prep_kernel(const PrepParams p) {
-    __shared__ float red[6][8];
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {           // 4 bits -> every third bit
+    v = (v | (v << 8)) & 0x0000F00Fu;
+    v = (v | (v << 4)) & 0x000C30C3u;
+    v = (v | (v << 2)) & 0x00249249u;
+    return v;
+}
+// Hilbert index of a cell (Skilling's axes-to-transpose, 3 axes x SORT_BITS bits): consecutive indices are face-adjacent
+// cells, so a run of consecutive sorted points never straddles a jump of the curve (a Morton run does: its chunks came
+// out with twice the radius and twice the candidates, tools/chunk_search_estimate.py).
+__device__ __forceinline__ uint32_t hilbert_code(uint32_t x0, uint32_t x1, uint32_t x2) {
+    constexpr uint32_t M = 1u << (SORT_BITS - 1);
+#pragma unroll
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+        if (x0 & Q) x0 ^= P;
+        if (x1 & Q) x0 ^= P; else { const uint32_t t = (x0 ^ x1) & P; x0 ^= t; x1 ^= t; }
+        if (x2 & Q) x0 ^= P; else { const uint32_t t = (x0 ^ x2) & P; x0 ^= t; x2 ^= t; }
+    }
+    x1 ^= x0; x2 ^= x1;
+    uint32_t t = 0;
+#pragma unroll
+    for (uint32_t Q = M; Q > 1; Q >>= 1) if (x2 & Q) t ^= Q - 1;
+    x0 ^= t; x1 ^= t; x2 ^= t;
+    return (spread3(x0) << 2) | (spread3(x1) << 1) | spread3(x2);
+}
+__device__ __forceinline__ int cell_of(float v, float lo, float inv) {
+    const float t = (v - lo) * inv;
+    int c = (t >= 0.f) ? (int)fminf(t, (float)((1 << SORT_BITS) - 1)) : 0;      // NaN -> 0
+    return c;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+chamfer_sort_kernel(const SortParams p) {
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    __shared__ float red[12][32];
+    __shared__ float s_box[12];                  // own lo/hi, other lo/hi
     __shared__ float s_meta[8];
+    __shared__ int s_bad;
+    __shared__ float s_sum;
+    __shared__ uint32_t warp_tot[32];
     pdl_trigger();
     pdl_wait();
-    const int b = blockIdx.y, tid = threadIdx.x;
-    const float* P = p.xyz1 + (size_t)b * p.n * 3;
-    const float* Q = p.xyz2 + (size_t)b * p.m * 3;
-    // this thread's own rows first (raw coordinates into registers): their trip to L2 / DRAM then overlaps the
-    // bounding-box pass instead of following it
-    constexpr int PRE = 2;
-    float prx[PRE], pry[PRE], prz[PRE];
-    {
-        const int total_rows = p.n_pad + p.m_pad;
+#ifdef SPK_TIMING
+    long long tph[8]; int nph = 0;
+#define SORT_PHASE() do { __syncthreads(); tph[nph++] = clock64(); } while (0)
+#else
+#define SORT_PHASE()
+#endif
+    const int cl = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    SORT_PHASE();
+    const int n = p.n[cl], n_pad = p.n_pad[cl], nc = p.nc[cl], nc_pad = p.nc_pad[cl];
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sort_smem);                              // SORT_CELLS
+    uint32_t* cellrank = hist + SORT_CELLS;                                                  // n
+    uint16_t* perm = reinterpret_cast<uint16_t*>(cellrank + ((n + 3) & ~3));                 // n
+    // the cloud's raw coordinates, staged by the bounding-box pass when they fit (the later phases then never wait for
+    // global memory: cells + histogram 3.8k -> cycles, sorted rows 9.1k -> at n = 2048)
+    float* raw = p.stage ? reinterpret_cast<float*>(perm + ((n + 7) & ~7)) : nullptr;                // 3 n
+    for (int i = tid; i < SORT_CELLS; i += SORT_THREADS) hist[i] = 0;
+
+    // ---- bounding boxes of both clouds (own first), non-finite detection --------------------------------------
+    int bad = 0;
 #pragma unroll
-        for (int j = 0; j < PRE; ++j) {
-            const int i = blockIdx.x * 256 + tid + j * (int)gridDim.x * 256;
-            prx[j] = pry[j] = prz[j] = 0.f;
-            if (i < total_rows) {
-                const bool first = i < p.n_pad;
-                const int r = first ? i : i - p.n_pad;
-                if (r < (first ? p.n : p.m)) {
-                    const float* sp = (first ? P : Q) + 3 * (size_t)r;
-                    prx[j] = __ldg(sp); pry[j] = __ldg(sp + 1); prz[j] = __ldg(sp + 2);
-                }
-            }
-        }
-    }
-    // bounding box over both clouds (every CTA of the sample recomputes it: 12*(n+m) bytes from L2).
-    // 128-bit loads, three per step = four whole points, so the axis of every lane is static.
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    int bad = 0;                                        // a NaN / inf coordinate anywhere in the sample
-    auto upd = [&](int a, float v) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); bad |= !(fabsf(v) < INFINITY); };
     for (int c = 0; c < 2; ++c) {
-        const float* X = c ? Q : P;
-        const int cnt = c ? p.m : p.n;
+        const int which = c == 0 ? cl : 1 - cl;
+        const float* X = p.xyz[which] + (size_t)b * p.n[which] * 3;
+        const int cnt = p.n[which];
+        float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+        auto upd = [&](int a, float v) { l[a] = fminf(l[a], v); h[a] = fmaxf(h[a], v); bad |= !(fabsf(v) < INFINITY); };
         int done = 0;
-        if ((((uintptr_t)X) & 15) == 0) {
-            const int steps = cnt / 4;                               // 4 points = 12 floats = 3 float4
+        if ((((uintptr_t)X) & 15) == 0) {                       // 4 points = 12 floats = 3 float4: the axis of every lane is static
+            const int steps = cnt / 4;
             const float4* X4 = reinterpret_cast<const float4*>(X);
-            for (int st = tid; st < steps; st += 256) {
+            for (int st = tid; st < steps; st += SORT_THREADS) {
                 const float4 a = __ldg(X4 + 3 * st), b4 = __ldg(X4 + 3 * st + 1), c4 = __ldg(X4 + 3 * st + 2);
+                if (c == 0 && raw != nullptr) {
+                    float4* r4 = reinterpret_cast<float4*>(raw) + 3 * st;
+                    r4[0] = a; r4[1] = b4; r4[2] = c4;
+                }
                 upd(0, a.x); upd(1, a.y); upd(2, a.z); upd(0, a.w);
                 upd(1, b4.x); upd(2, b4.y); upd(0, b4.z); upd(1, b4.w);
                 upd(2, c4.x); upd(0, c4.y); upd(1, c4.z); upd(2, c4.w);
             }
             done = steps * 4;
         }
-        for (int i = done + tid; i < cnt; i += 256) { upd(0, __ldg(X + 3 * i)); upd(1, __ldg(X + 3 * i + 1)); upd(2, __ldg(X + 3 * i + 2)); }
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-        for (int d = 16; d > 0; d >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], d));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], d));
+        for (int i = done + tid; i < cnt; i += SORT_THREADS) {
+            const float x = __ldg(X + 3 * i), y = __ldg(X + 3 * i + 1), z = __ldg(X + 3 * i + 2);
+            if (c == 0 && raw != nullptr) { raw[3 * i] = x; raw[3 * i + 1] = y; raw[3 * i + 2] = z; }
+            upd(0, x); upd(1, y); upd(2, z);
         }
-    if ((tid & 31) == 0)
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { red[a][tid >> 5] = lo[a]; red[3 + a][tid >> 5] = hi[a]; }
-    bad = __syncthreads_or(bad);
-    if (tid == 0) {
-        float L[3], H[3];
         for (int a = 0; a < 3; ++a) {
-            L[a] = red[a][0]; H[a] = red[3 + a][0];
-            for (int w = 1; w < 8; ++w) { L[a] = fminf(L[a], red[a][w]); H[a] = fmaxf(H[a], red[3 + a][w]); }
+            for (int d = 16; d > 0; d >>= 1) {
+                l[a] = fminf(l[a], __shfl_xor_sync(0xFFFFFFFFu, l[a], d));
+                h[a] = fmaxf(h[a], __shfl_xor_sync(0xFFFFFFFFu, h[a], d));
+            }
+            if (lane == 0) { red[6 * c + a][warp] = l[a]; red[6 * c + 3 + a][warp] = h[a]; }
         }
+    }
+    bad = __syncthreads_or(bad);
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            float v = red[k][lane];
+            const bool is_lo = (k % 6) < 3;
+            for (int d = 16; d > 0; d >>= 1) {
+                const float o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+                v = is_lo ? fminf(v, o) : fmaxf(v, o);
+            }
+            if (lane == 0) s_box[k] = v;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
         float c[3], ext = 0.f, amax = 0.f;
         for (int a = 0; a < 3; ++a) {
-            c[a] = 0.5f * L[a] + 0.5f * H[a];
-            ext = fmaxf(ext, fmaxf(H[a] - c[a], c[a] - L[a]));
-            amax = fmaxf(amax, fmaxf(fabsf(L[a]), fabsf(H[a])));
+            const float L = fminf(s_box[a], s_box[6 + a]), H = fmaxf(s_box[3 + a], s_box[9 + a]);
+            c[a] = 0.5f * L + 0.5f * H;
+            ext = fmaxf(ext, fmaxf(H - c[a], c[a] - L));
+            amax = fmaxf(amax, fmaxf(fabsf(L), fabsf(H)));
         }
         // scale = 2^-ceil(log2(ext)) so that |x - c| * scale <= 1; degenerate / non-finite boxes -> 1
         float scale = 1.f;
         if (ext > 0.f && ext < INFINITY) {
-            int e; (void)frexpf(ext, &e);                 // ext = f * 2^e, f in [0.5, 1)
+            int e = ((__float_as_int(ext) >> 23) & 255) - 126;       // ext = f * 2^e, f in [0.5, 1) (denormals end up at the clamp)
             e = max(-100, min(100, e));
-            scale = ldexpf(1.f, -e);
+            scale = __int_as_float((127 - e) << 23);
         }
-        // error budget of the approximate block, scaled units: fp16 hi/lo products + fp32 accumulate
-        // (2^-17) plus the rounding of the centred coordinates themselves (|x| * 2^-23 * scale each)
+        // error budget of V in scaled units: fp16 hi/lo products + fp32-grade accumulation (2^-17) plus the rounding
+        // of the centred coordinates themselves (|x| * 2^-23 * scale each)
         const float delta = amax * scale * 1.1920929e-7f;
         const float e_tot = 7.62939453125e-6f + 16.f * delta;
-        s_meta[0] = c[0]; s_meta[1] = c[1]; s_meta[2] = c[2]; s_meta[3] = scale;
-        s_meta[4] = 2.f * e_tot; s_meta[5] = scale * scale;
-        // bias: a power of two above the error bound, so that every approximate distance is a POSITIVE fp16
-        // (its bit pattern then orders like its value); 2^-6 unless the coordinates are badly conditioned
-        float bias = 0.015625f;
-        while (bias < 4.f * e_tot && bias < 1024.f) bias *= 2.f;
-        s_meta[6] = bias;
-        if (blockIdx.x == 0) {
+        // the bias of the chunk rows (a power of two <= 1024) must stay above the radius cap + error bound
+        const bool hopeless = !(TC_RCAP_MAX + 4.f * e_tot <= 1024.f) || !(scale * scale > 0.f) || !(scale * scale < INFINITY);
+        s_meta[0] = c[0]; s_meta[1] = c[1]; s_meta[2] = c[2]; s_meta[3] = scale; s_meta[4] = 2.f * e_tot; s_meta[5] = scale * scale;
+        s_bad = (bad || hopeless) ? 1 : 0;
+        if (cl == 0) {
             ChamferMeta mm; mm.cx = c[0]; mm.cy = c[1]; mm.cz = c[2]; mm.scale = scale; mm.tau = 2.f * e_tot;
-            mm.scale2 = scale * scale; mm.bias = bias;
-            mm.nonfinite = (bad || !(bias >= 4.f * e_tot)) ? 1.f : 0.f;     // hopeless conditioning counts as non-finite
+            mm.scale2 = scale * scale; mm.bias = 0.f; mm.nonfinite = s_bad ? 1.f : 0.f;
             p.meta[b] = mm;
+            if (p.loss != nullptr) p.loss[b] = 0.f;
         }
     }
     __syncthreads();
-    const float cx = s_meta[0], cy = s_meta[1], cz = s_meta[2], sc = s_meta[3], bias = s_meta[6];
-    unsigned char* A1 = p.A1 + (size_t)b * p.n_pad * 32; unsigned char* B1 = p.B1 + (size_t)b * p.n_pad * 32;
-    unsigned char* A2 = p.A2 + (size_t)b * p.m_pad * 32; unsigned char* B2 = p.B2 + (size_t)b * p.m_pad * 32;
-    const int total = p.n_pad + p.m_pad;
-    int it_pre = 0;
-    for (int i = blockIdx.x * 256 + tid; i < total; i += gridDim.x * 256, ++it_pre) {
-        const bool first = i < p.n_pad;
-        const int r = first ? i : i - p.n_pad;
-        const bool real = r < (first ? p.n : p.m);
-        float ux = 0.f, uy = 0.f, uz = 0.f;
-        float4 raw = make_float4(INFINITY, INFINITY, INFINITY, 0.f);      // padding: infinitely far in the exact pass
-        if (real) {
-            const float* s = (first ? P : Q) + 3 * (size_t)r;
-            if (it_pre == 0) { raw.x = prx[0]; raw.y = pry[0]; raw.z = prz[0]; }
-            else if (it_pre == 1) { raw.x = prx[1]; raw.y = pry[1]; raw.z = prz[1]; }
-            else { raw.x = __ldg(s); raw.y = __ldg(s + 1); raw.z = __ldg(s + 2); }
-            ux = (raw.x - cx) * sc; uy = (raw.y - cy) * sc; uz = (raw.z - cz) * sc;
-        }
-        write_rows(first ? A1 : A2, first ? B1 : B2, r, real, ux, uy, uz, bias);
-        (first ? p.T1 + (size_t)b * p.n_pad : p.T2 + (size_t)b * p.m_pad)[r] = raw;
-        if (real && p.packed1 != nullptr)
-            (first ? p.packed1 + (size_t)b * p.n : p.packed2 + (size_t)b * p.m)[r] = ~0ull;
+    SORT_PHASE();                 // 1: bounding boxes + meta
+    if (s_bad) return;            // the search kernel walks the original arrays in reference order: nothing to sort
+    const float* X = raw != nullptr ? raw : p.xyz[cl] + (size_t)b * n * 3;       // (shared or global: plain loads from here on)
+    const float cx = s_meta[0], cy = s_meta[1], cz = s_meta[2], sc = s_meta[3], sc2 = s_meta[5];
+
+    // ---- counting sort by Morton cell of the cloud's own bounding box --------------------------------------------
+    float inv[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float e = s_box[3 + a] - s_box[a];
+        inv[a] = e > 0.f ? (float)(1 << SORT_BITS) / e : 0.f;
+        if (!(inv[a] < INFINITY)) inv[a] = 0.f;
     }
-    if (p.counters != nullptr && blockIdx.x == 0)
-        for (int i = tid; i < p.n_counters; i += 256) p.counters[(size_t)b * p.n_counters + i] = 0;
-    if (p.loss != nullptr && blockIdx.x == 0 && tid == 0) p.loss[b] = 0.f;
+    for (int i = tid; i < n; i += SORT_THREADS) {
+        const float x = X[3 * i], y = X[3 * i + 1], z = X[3 * i + 2];
+        const uint32_t code = hilbert_code((uint32_t)cell_of(x, s_box[0], inv[0]), (uint32_t)cell_of(y, s_box[1], inv[1]), (uint32_t)cell_of(z, s_box[2], inv[2]));
+        const uint32_t rank = atomicAdd(&hist[code], 1u);
+        cellrank[i] = (code << 16) | rank;
+    }
+    __syncthreads();
+    SORT_PHASE();                 // 2: cells + histogram
+    {   // exclusive scan of the SORT_CELLS counters: SORT_CELLS / SORT_THREADS consecutive cells per thread
+        constexpr int PER = SORT_CELLS / SORT_THREADS;
+        uint32_t v[PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { v[k] = hist[tid * PER + k]; sum += v[k]; }
+        uint32_t incl = sum;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t t = warp_tot[lane], it = t;
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, it, d); if (lane >= d) it += o; }
+            warp_tot[lane] = it - t;
+        }
+        __syncthreads();
+        uint32_t run = warp_tot[warp] + incl - sum;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { hist[tid * PER + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    SORT_PHASE();                 // 3: scan
+    {   // the search kernel starts every query at the chunk of its own cell ("home" chunk)
+        uint16_t* cs = p.cellstart[cl] + (size_t)b * SORT_CELLS;
+        for (int i = tid; i < SORT_CELLS; i += SORT_THREADS) cs[i] = (uint16_t)hist[i];
+    }
+    for (int i = tid; i < n; i += SORT_THREADS) {
+        const uint32_t cr = cellrank[i];
+        perm[hist[cr >> 16] + (cr & 0xFFFFu)] = (uint16_t)i;
+    }
+    __syncthreads();
+
+    SORT_PHASE();                 // 4: cell starts + permutation
+    // ---- sorted outputs: points, query operand rows, per-chunk box / centre / radius ------------------------------------
+    float4* S = p.S[cl] + (size_t)b * nc_pad * TC_CHUNK;
+    unsigned char* A = p.A[cl] + (size_t)b * n_pad * 32;
+    unsigned char* Bc = p.Bc[cl] + (size_t)b * nc_pad * 32;
+    float4* box = p.box[cl] + (size_t)b * nc_pad * 2;
+    float4* cst = reinterpret_cast<float4*>(cellrank);          // per chunk (centre, 1.5 r^2 scaled); cellrank is dead: n * 4 >= nc * 16 bytes
+    if (tid == 0) s_sum = 0.f;
+    __syncthreads();
+    float sub_sum = 0.f;
+    for (int s = tid; s < n_pad; s += SORT_THREADS) {
+        const bool real = s < n;
+        float x = INFINITY, y = INFINITY, z = INFINITY;
+        int orig = 0x7FFFFFFF;
+        if (real) {
+            orig = perm[s];
+            x = X[3 * orig]; y = X[3 * orig + 1]; z = X[3 * orig + 2];
+        }
+        S[s] = make_float4(x, y, z, __int_as_float(orig));
+        write_a_row(A, s, real, (x - cx) * sc, (y - cy) * sc, (z - cz) * sc);
+        // chunk = 16 consecutive lanes
+        float l[3] = {x, y, z}, h[3] = {real ? x : -INFINITY, real ? y : -INFINITY, real ? z : -INFINITY};   // (!real: x = y = z = +inf)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            for (int d = 8; d > 0; d >>= 1) {
+                l[a] = fminf(l[a], __shfl_xor_sync(0xFFFFFFFFu, l[a], d));
+                h[a] = fmaxf(h[a], __shfl_xor_sync(0xFFFFFFFFu, h[a], d));
+            }
+        const float ccx = 0.5f * l[0] + 0.5f * h[0], ccy = 0.5f * l[1] + 0.5f * h[1], ccz = 0.5f * l[2] + 0.5f * h[2];
+        float r2 = 0.f;
+        if (real) { const float dx = x - ccx, dy = y - ccy, dz = z - ccz; r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy)); }
+        for (int d = 8; d > 0; d >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xFFFFFFFFu, r2, d));
+        const int chunk = s >> 4;
+        if ((lane & 15) == 0 && chunk < nc) {
+            const float sub = 1.5f * r2 * sc2 * 1.001f;          // 1.5 r^2 in scaled units, inflated for the rounding of r2 itself
+            cst[chunk] = make_float4(ccx, ccy, ccz, sub);
+            box[2 * chunk] = make_float4(l[0], l[1], l[2], 0.f);
+            box[2 * chunk + 1] = make_float4(h[0], h[1], h[2], 0.f);
+            sub_sum += fminf(sub, 4.f);
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) sub_sum += __shfl_xor_sync(0xFFFFFFFFu, sub_sum, d);
+    if (lane == 0 && sub_sum != 0.f) atomicAdd(&s_sum, sub_sum);
+    __syncthreads();
+    SORT_PHASE();                 // 5: sorted points, query rows, chunk stats
+    // ---- chunk operand rows.  The radius term folded into a row is capped at 3x the cloud's mean (outliers: chunks that
+    // straddle a sparse region) -- capped chunks are flagged and always go to the box test -- and the bias, a power of two
+    // above the cap + error bound, keeps every V a POSITIVE fp16 (its bit pattern then orders like its value).
+    const float cap = fminf(fmaxf(3.f * s_sum / (float)nc, 1.f / 1024.f), TC_RCAP_MAX);
+    const float e4 = 2.f * s_meta[4];                             // 4 e_tot
+    float bias = 1.f / 64.f;
+    while (bias < cap + e4 && bias < 1024.f) bias *= 2.f;
+    if (tid == 0) {
+        ChamferGrid gi;
+        for (int a = 0; a < 3; ++a) { gi.lo[a] = s_box[a]; gi.inv[a] = inv[a]; }
+        gi.bias = bias; gi.pad = 0.f;
+        p.grid[cl][b] = gi;
+    }
+    for (int c = tid; c < nc_pad; c += SORT_THREADS) {
+        if (c < nc) {
+            const float4 ci = cst[c];
+            const bool capped = !(ci.w <= cap);
+            write_b_row(Bc, c, true, (ci.x - cx) * sc, (ci.y - cy) * sc, (ci.z - cz) * sc, capped ? cap : ci.w, bias);
+            if (capped) box[2 * c].w = 1.f;
+        } else {
+            write_b_row(Bc, c, false, 0.f, 0.f, 0.f, 0.f, 0.f);
+            box[2 * c] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
+            box[2 * c + 1] = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+        }
+    }
+    SORT_PHASE();                 // 6: chunk rows
+#ifdef SPK_TIMING
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+        printf("sort kernel phases (cycles): bbox+meta %lld, cells+hist %lld, scan %lld, perm %lld, sorted rows %lld, chunk rows %lld\n",
+               tph[1] - tph[0], tph[2] - tph[1], tph[3] - tph[2], tph[4] - tph[3], tph[5] - tph[4], tph[6] - tph[5]);
+#endif
     pdl_tail_trigger();
 }
 
@@ -276,9 +424,9 @@ __device__ __forceinline__ uint64_t umma_smem_desc(const void* smem_ptr) {
     d |= (uint64_t)1 << 46;
     return d;
 }
-// kind::f16: A, B = F16 (0), D = F16 (0: one fp16 per 32-bit TMEM column), both K-major, M = 128, N = TC_N.
-// A single K=16 instruction forms the whole distance, so the only fp16 rounding is the final one.
-constexpr uint32_t TC_IDESC = (0u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::f16: A, B = F16 (0), D = F16 (0: one fp16 per 32-bit TMEM column), both K-major, M = 128, N = TC_NC.
+// A single K=16 instruction forms the whole value, so the only fp16 rounding is the final one.
+constexpr uint32_t TC_IDESC = (0u << 4) | ((uint32_t)(TC_NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
     asm volatile(
@@ -291,33 +439,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 // 32 columns of fp16 accumulators -> 16 registers, two columns per register (even column in the low half)
 __device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -328,473 +449,469 @@ __device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
-// minimum of 16 packed words, per 16-bit lane (positive fp16 bit patterns order like their values):
-// VIMNMX3.U16x2, four new elements per instruction -- twice the rate of the fp32 FMNMX3 (tools/micro/minbench.cu)
-__device__ __forceinline__ uint32_t pmin16(const uint32_t* w) {
-    uint32_t m0 = __vimin3_u16x2(w[0], w[1], w[2]), m1 = __vimin3_u16x2(w[3], w[4], w[5]);
-    m0 = __vimin3_u16x2(m0, w[6], w[7]); m1 = __vimin3_u16x2(m1, w[8], w[9]);
-    m0 = __vimin3_u16x2(m0, w[10], w[11]); m1 = __vimin3_u16x2(m1, w[12], w[13]);
-    return __vimin3_u16x2(m0, m1, __vminu2(w[14], w[15]));
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float min3(float a, float b, float c) {
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
-__device__ __forceinline__ float min32(const float* v) {
-    float m0 = min3(v[0], v[1], v[2]), m1 = min3(v[3], v[4], v[5]), m2 = min3(v[6], v[7], v[8]), m3 = min3(v[9], v[10], v[11]);
-    m0 = min3(m0, v[12], v[13]); m1 = min3(m1, v[14], v[15]); m2 = min3(m2, v[16], v[17]); m3 = min3(m3, v[18], v[19]);
-    m0 = min3(m0, v[20], v[21]); m1 = min3(m1, v[22], v[23]); m2 = min3(m2, v[24], v[25]); m3 = min3(m3, v[26], v[27]);
-    m0 = min3(m0, v[28], v[29]); m1 = min3(m1, v[30], v[31]);
-    return fminf(min3(m0, m1, m2), m3);
-}
-__device__ __forceinline__ float ref_sqdist_tc(float x1, float y1, float z1, float x2, float y2, float z2) {
-    const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
-    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-}
-__device__ __forceinline__ void exact_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four exact warps
-
-// ---------------------------------------------------------------------------------------------
-// main kernel
-// ---------------------------------------------------------------------------------------------
-struct TcParams {
-    const float* xyz1; const float* xyz2;
-    const unsigned char* A1; const unsigned char* B1; const unsigned char* A2; const unsigned char* B2;
-    const float4* T1; const float4* T2;
-    const ChamferMeta* meta;
-    float* dist1; float* dist2; int32_t* idx1; int32_t* idx2;
-    int B, n, m, n_pad, m_pad;
-    int tiles1, tiles2;      // query tiles per sample in direction 0 / 1
-    int S1, S2;              // target-range splits per query tile in direction 0 / 1 (1 = whole range in one job)
-    unsigned long long* packed1; unsigned long long* packed2; int* counters;    // merge of split jobs
-    float* loss;             // fused loss (or NULL): (B) accumulators zeroed by the prep kernel
-};
-
-struct __align__(128) TcSmem {
-    unsigned char a_tile[2][TC_TILE_BYTES];                    // double-buffered: the next job's queries arrive early
-    unsigned char b_tile[TC_STAGES][TC_TILE_BYTES];
-    float4 t4[TC_T4_BUFS][TC_SB_TARGETS];                      // raw target coordinates, per super-block
-    uint32_t cm[2][TC_CM_WORDS * TC_TILE];                     // packed chunk minima of a super-block, [word][row]
-    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full[2], a_empty[2], tmem_full[TC_NBUF], tmem_empty[TC_NBUF], t4_full[TC_T4_BUFS], t4_empty[TC_T4_BUFS],
-             cm_full[2], cm_empty[2];
-    uint32_t tmem_base;
-    int dbg[2];
-    int last;                             // split jobs: this CTA finished the query tile's last sub-job
-};
-
 __device__ __forceinline__ float min16(const float* v) {
     float m0 = min3(v[0], v[1], v[2]), m1 = min3(v[3], v[4], v[5]);
     m0 = min3(m0, v[6], v[7]); m1 = min3(m1, v[8], v[9]);
     m0 = min3(m0, v[10], v[11]); m1 = min3(m1, v[12], v[13]);
     return min3(m0, m1, fminf(v[14], v[15]));
 }
-
-// ---- fused loss (train.py:68-69: mean(dist1,1) + mean(dist2,1)) -------------------------------------------------
-// Every exact warp adds its 32 rows' distances (shuffles), scales by 1/n or 1/m and adds the result to
-// loss[b] with ONE fire-and-forget float reduction (red.global.add.f32: no return value, nothing waits
-// for it).  (A deterministic variant -- partial sums parked per (tile, warp), an acq_rel ticket counter,
-// the last arrival summing in fixed order -- was measured 5 us slower at config A: the acquire holds the
-// next job's loads back.)
-__device__ __forceinline__ void loss_contribute(const TcParams& p, int b, int dir, int lane, float v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-    if (lane == 0) atomicAdd(p.loss + b, v / (float)(dir ? p.m : p.n));
+__device__ __forceinline__ float ref_sqdist_tc(float x1, float y1, float z1, float x2, float y2, float z2) {
+    const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
-chamfer_tc_kernel(const TcParams p) {
+// NmDistanceKernel statement for statement (reference chamfer.cu:16-129): targets in batches of 512, the batch's
+// first target initialises the running best (`k==0 || d<best`), the stored result is replaced only when strictly
+// greater (`k2==0 || result>best`).  Used for samples with non-finite coordinates / hopeless conditioning, where the
+// result depends on exactly this order (a NaN distance at a batch start hides the rest of that batch).
+__device__ __forceinline__ void ref_order_nn(const float* __restrict__ T, int nt, float qx, float qy, float qz, float& res, int& res_i) {
+    res = 0.f; res_i = 0;
+    for (int k2 = 0; k2 < nt; k2 += 512) {
+        const int end_k = min(nt, k2 + 512) - k2;
+        float best = 0.f; int best_i = 0;
+        for (int k = 0; k < end_k; ++k) {
+            const float* t = T + 3 * (size_t)(k2 + k);
+            const float d = ref_sqdist_tc(qx, qy, qz, __ldg(t), __ldg(t + 1), __ldg(t + 2));
+            if (k == 0 || d < best) { best = d; best_i = k + k2; }
+        }
+        if (k2 == 0 || res > best) { res = best; res_i = best_i; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// search kernel
+// ---------------------------------------------------------------------------------------------
+struct SearchParams {
+    const float* xyz[2];
+    int n[2], n_pad[2], nc[2], nc_pad[2];
+    const float4* S[2]; const unsigned char* A[2]; const unsigned char* Bc[2]; const float4* box[2];
+    const uint16_t* cellstart[2]; const ChamferGrid* grid[2];
+    const ChamferMeta* meta;
+    float* dist[2]; int32_t* idx[2];
+    float* loss;                 // fused loss (or NULL): (B) accumulators zeroed by the sort kernel
+    int B, tiles[2];
+};
+
+#ifdef SPK_TIMING
+__device__ unsigned long long g_tc_dbg[8];      // 0 queries x passes, 1 step-1 mask bits, 2 step-2 mask bits, 3 box tests, 4 chunk evaluations, 5 warp-max evaluations
+#define TC_COUNT(i, v) atomicAdd(&g_tc_dbg[i], (unsigned long long)(v))
+#else
+#define TC_COUNT(i, v)
+#endif
+
+constexpr int TC_PASS_TARGETS = TC_NC * TC_CHUNK;          // 2048 sorted targets per pass
+constexpr int TC_QCAP = 1536;                              // candidate queue slots per pass (overflow: the owner evaluates at once)
+
+struct __align__(128) SearchSmem {
+    unsigned char a_tile[TC_TILE_BYTES];         // query operand tile of the job whose MMAs are being issued
+    unsigned char b_tile[2][TC_TILE_BYTES];      // chunk-centre operand tile, per step parity
+    float4 box[TC_NC * 2];                       // this pass's chunk boxes {lo, flag}, {hi, 0}
+    float4 tgt[TC_PASS_TARGETS];                 // this pass's sorted targets (x, y, z, original index)
+    float4 q4[TC_TILE];                          // this job's queries (x, y, z, original index)
+    unsigned long long best[TC_TILE];            // per query (distance bits << 32) | original target index: its 64-bit minimum IS the first minimum
+    uint16_t queue[TC_QCAP];                     // (query row << 7) | chunk of the pass: candidates waiting for the box test + exact evaluation
+    uint64_t a_full, b_full[2], mma_done, t_full;
+    uint32_t tmem_base;
+    uint32_t big[4];                             // this pass's capped chunks (always box-tested)
+    uint32_t qn;                                 // queue fill
+};
+
+// per lane (0x8000 | t) - v keeps bit 15 exactly when v <= t (both 15-bit values: no borrow crosses the lanes);
+// bits 15 / 31 of word i go to mask bits i / 16+i  -> bit u of m[g] <=> chunk 32 g + u of the pass
+__device__ __forceinline__ void build_mask(const uint32_t* w, uint32_t t16, uint32_t* m) {
+    const uint32_t T2 = (t16 * 0x10001u) | 0x80008000u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t mm = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mm |= ((T2 - w[16 * g + i]) >> (15 - i)) & (0x10001u << i);
+        m[g] = mm;
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 4)
+chamfer_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
+    SearchSmem& S = *reinterpret_cast<SearchSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int jobs_per_sample = p.tiles1 * p.S1 + p.tiles2 * p.S2;
+    const int jobs_per_sample = p.tiles[0] + p.tiles[1];
     const int total_jobs = jobs_per_sample * p.B;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1); }
-        for (int i = 0; i < TC_NBUF; ++i) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], TC_MIN_WARPS); }
-        for (int i = 0; i < TC_T4_BUFS; ++i) { mbar_init(&S.t4_full[i], 1); mbar_init(&S.t4_empty[i], TC_EXACT_WARPS); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&S.cm_full[i], TC_MIN_WARPS); mbar_init(&S.cm_empty[i], TC_EXACT_WARPS); }
+        for (int i = 0; i < 2; ++i) mbar_init(&S.b_full[i], 1);
+        mbar_init(&S.a_full, 1); mbar_init(&S.mma_done, 1); mbar_init(&S.t_full, 1);
         fence_mbar_init();
-#ifdef SPK_TIMING
-        S.dbg[0] = 0; S.dbg[1] = 0;
-#endif
     }
-    if (warp == 1) {   // TMEM: 256 columns (2 x 128-column fp32 accumulators)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(256));
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(TC_NC));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-#ifdef SPK_TIMING
-    const long long tk0 = clock64();
-    __shared__ long long tlog_t[320]; __shared__ int tlog_a[320]; __shared__ int tlog_b[320]; __shared__ const char* tlog_s[320]; __shared__ int tlog_n;
-    if (tid == 0) tlog_n = 0;
-#define TCLOG(tag, a, b) do { if (blockIdx.x == 0 && (warp == 2 || warp == 6) && lane == 0) { const int ti_ = atomicAdd(&tlog_n, 1); if (ti_ < 320) { tlog_t[ti_] = clock64() - tk0; tlog_s[ti_] = tag; tlog_a[ti_] = (int)(a) + 1000 * (warp == 6); tlog_b[ti_] = (int)(b); } } } while (0)
-#define TCLOGF(tag, a, b) do { if (blockIdx.x == 0 && lane == 0 && job_it == 1) { const int ti_ = atomicAdd(&tlog_n, 1); if (ti_ < 320) { tlog_t[ti_] = clock64() - tk0; tlog_s[ti_] = tag; tlog_a[ti_] = (int)(a); tlog_b[ti_] = (int)(b); } } } while (0)
-#else
-#define TCLOG(tag, a, b)
-#define TCLOGF(tag, a, b)
-#endif
     const uint32_t tmem_base = S.tmem_base;
-    pdl_wait();                  // operands / metadata come from chamfer_prep_kernel
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    pdl_wait();                  // operands / metadata come from chamfer_sort_kernel
 
-    // running counters (identical in every role): B-ring slots, accumulator buffers, super-blocks, jobs
-    uint32_t ring_it = 0, acc_it = 0, sb_it = 0, job_it = 0;
-
-    for (int job_id = blockIdx.x; job_id < total_jobs; job_id += gridDim.x, ++job_it) {
-        const int b = (int)((unsigned)job_id / (unsigned)jobs_per_sample);
-        int job = job_id - b * jobs_per_sample;
-        const int dir = job < p.tiles1 * p.S1 ? 0 : 1;
-        if (dir) job -= p.tiles1 * p.S1;
-        const int NS = dir ? p.S2 : p.S1;
-        const int nq = dir ? p.m : p.n, nt = dir ? p.n : p.m;
-        const int nq_pad = dir ? p.m_pad : p.n_pad, nt_pad = dir ? p.n_pad : p.m_pad;
-        const int n_sb_all = nt_pad / TC_SB_TARGETS;           // rows are padded to whole super-blocks
-        int sb0 = 0, sb1 = n_sb_all;
-        if (NS > 1) {                                          // (the common unsplit case pays no divisions)
-            const int split = (int)((unsigned)job % (unsigned)NS);      // sub-jobs of one query tile are neighbours:
-            job = (int)((unsigned)job / (unsigned)NS);                  // they run together and share the A tile in L2
-            sb0 = split * n_sb_all / NS; sb1 = (split + 1) * n_sb_all / NS;
+    // decode a job id
+    auto decode = [&](int job_id, int& b, int& dir, int& tile) {
+        b = (int)((unsigned)job_id / (unsigned)jobs_per_sample);
+        tile = job_id - b * jobs_per_sample;
+        dir = tile < p.tiles[0] ? 0 : 1;
+        if (dir) tile -= p.tiles[0];
+    };
+    // thread 0: bulk loads of the MMA operands of step (job, pass) into the stage of its parities
+    auto issue_loads = [&](int job_id, int pass, uint32_t step, uint32_t jobn) {
+        int b, dir, tile; decode(job_id, b, dir, tile);
+        const int tgt = 1 - dir;
+        if (pass == 0) {          // (single buffer: the caller issues this only after the previous job's last MMA has completed)
+            mbar_expect_tx(&S.a_full, TC_TILE_BYTES);
+            bulk_g2s(S.a_tile, p.A[dir] + ((size_t)b * p.n_pad[dir] + (size_t)tile * TC_TILE) * 32, TC_TILE_BYTES, &S.a_full);
         }
-        const int n_sb = sb1 - sb0;                            // super-blocks of this (sub-)job: [sb0, sb1)
-        const int T = n_sb * TC_SB_TILES;                      // target tiles of this (sub-)job
+        mbar_expect_tx(&S.b_full[step & 1], TC_TILE_BYTES);
+        bulk_g2s(S.b_tile[step & 1], p.Bc[tgt] + ((size_t)b * p.nc_pad[tgt] + (size_t)pass * TC_NC) * 32, TC_TILE_BYTES, &S.b_full[step & 1]);
+    };
+    // thread 0: this pass's chunk boxes and sorted targets (one stage: issued once every thread is done with the previous pass)
+    auto issue_targets = [&](int job_id, int pass) {
+        int b, dir, tile; decode(job_id, b, dir, tile);
+        const int tgt = 1 - dir;
+        mbar_expect_tx(&S.t_full, (uint32_t)(sizeof(S.box) + sizeof(S.tgt)));
+        bulk_g2s(S.box, p.box[tgt] + ((size_t)b * p.nc_pad[tgt] + (size_t)pass * TC_NC) * 2, (uint32_t)sizeof(S.box), &S.t_full);
+        bulk_g2s(S.tgt, p.S[tgt] + (size_t)b * p.nc_pad[tgt] * TC_CHUNK + (size_t)pass * TC_PASS_TARGETS, (uint32_t)sizeof(S.tgt), &S.t_full);
+    };
+    auto issue_mma = [&](uint32_t step, uint32_t jobn, bool first_pass) {
+        if (first_pass) mbar_wait(&S.a_full, jobn & 1);
+        mbar_wait(&S.b_full[step & 1], (step >> 1) & 1);
+        tc_fence_after();
+        umma_f16(tmem_base, umma_smem_desc(S.a_tile), umma_smem_desc(S.b_tile[step & 1]), TC_IDESC);
+        umma_commit(&S.mma_done);
+    };
+    // the step after (job, pass) of this CTA's static job list; false when there is none
+    auto next_step = [&](int& job_id, int& pass, uint32_t& jobn) -> bool {
+        int b, dir, tile; decode(job_id, b, dir, tile);
+        const int passes = p.nc_pad[1 - dir] / TC_NC;
+        if (pass + 1 < passes) { ++pass; return true; }
+        job_id += gridDim.x; pass = 0; ++jobn;
+        return job_id < total_jobs;
+    };
 
-        if (warp == 0) {
-            // ===== TMA producer =====
-            if (lane == 0) {
-                const unsigned char* Aop = (dir ? p.A2 : p.A1) + ((size_t)b * nq_pad + (size_t)job * TC_TILE) * 32;
-                const unsigned char* Bop = (dir ? p.B1 : p.B2) + ((size_t)b * nt_pad + (size_t)sb0 * TC_SB_TARGETS) * 32;
-                const float4* T4 = (dir ? p.T1 : p.T2) + (size_t)b * nt_pad + (size_t)sb0 * TC_SB_TARGETS;
-                const uint32_t ab = job_it & 1;
-                mbar_wait(&S.a_empty[ab], (uint32_t)(((job_it >> 1) & 1) ^ 1));   // the job two back has read this buffer
-                mbar_expect_tx(&S.a_full[ab], TC_TILE_BYTES);
-                bulk_g2s(S.a_tile[ab], Aop, TC_TILE_BYTES, &S.a_full[ab]);
-                for (int sb = 0; sb < n_sb; ++sb) {
-                    const uint32_t sbi = sb_it + sb, pb = sbi & 1;
-                    constexpr int tiles = TC_SB_TILES;
-                    for (int tt = 0; tt < tiles; ++tt) {
-                        const uint32_t it = ring_it + sb * TC_SB_TILES + tt, s = it % TC_STAGES;
-                        mbar_wait(&S.empty[s], (uint32_t)(((it / TC_STAGES) & 1) ^ 1));
-                        mbar_expect_tx(&S.full[s], TC_TILE_BYTES);
-                        bulk_g2s(S.b_tile[s], Bop + (size_t)(sb * TC_SB_TILES + tt) * TC_TILE_BYTES, TC_TILE_BYTES, &S.full[s]);
-                    }
-                    // raw coordinates for the exact pass: after the operand tiles, so that the exact warps (which
-                    // lag up to two super-blocks behind the MMAs) never hold the operand stream back
-                    const uint32_t tb = sbi % TC_T4_BUFS;
-                    mbar_wait(&S.t4_empty[tb], (uint32_t)(((sbi / TC_T4_BUFS) & 1) ^ 1));
-                    mbar_expect_tx(&S.t4_full[tb], (uint32_t)tiles * TC_TILE * 16u);
-                    bulk_g2s(S.t4[tb], T4 + (size_t)sb * TC_SB_TARGETS, (uint32_t)tiles * TC_TILE * 16u, &S.t4_full[tb]);
-                }
-            }
-        } else if (warp == 1) {
-            // ===== MMA issuer =====
-            if (lane == 0) {
-                const uint32_t ab = job_it & 1;
-                mbar_wait(&S.a_full[ab], (uint32_t)((job_it >> 1) & 1));
-                const uint64_t a_desc = umma_smem_desc(S.a_tile[ab]);
-                for (int t = 0; t < T; ++t) {
-                    const uint32_t it = ring_it + t, s = it % TC_STAGES;
-#if SPK_SPIN >= 1
-                    mbar_wait_spin(&S.full[s], (uint32_t)((it / TC_STAGES) & 1));
-#else
-                    mbar_wait(&S.full[s], (uint32_t)((it / TC_STAGES) & 1));
-#endif
-#pragma unroll
-                    for (int half = 0; half < TC_TILE / TC_N; ++half) {     // TC_TILE / TC_N MMAs per 128-target smem tile
-                        const uint32_t ai = acc_it + (TC_TILE / TC_N) * t + half, buf = ai % TC_NBUF;
-#if SPK_SPIN >= 1
-                        mbar_wait_spin(&S.tmem_empty[buf], (uint32_t)(((ai / TC_NBUF) & 1) ^ 1));
-#else
-                        mbar_wait(&S.tmem_empty[buf], (uint32_t)(((ai / TC_NBUF) & 1) ^ 1));
-#endif
-                        TCLOGF("M empty ok", ai, 0);
-                        tc_fence_after();
-                        umma_f16(tmem_base + buf * TC_N, a_desc, umma_smem_desc(S.b_tile[s] + half * (TC_N * 32)), TC_IDESC);
-                        umma_commit(&S.tmem_full[buf]);  // accumulator ready for the epilogue
-                        TCLOGF("M issued+commit", ai, 0);
-                    }
-                    umma_commit(&S.empty[s]);            // smem slot free once both MMAs have read it
-                }
-                umma_commit(&S.a_empty[ab]);             // this A buffer may be replaced
-            }
-        } else if (warp < 2 + TC_MIN_WARPS) {
-            // ===== min warps (4, one per TMEM lane quarter): accumulators -> packed chunk minima -> shared memory.
-            // They never wait for the filter / exact pass, so the TMEM read path -- the resource that paces this
-            // kernel -- stays busy; the exact warps follow up to two super-blocks behind.
-            const int q = warp & 3;
-            const int row = q * 32 + lane;                         // query row inside the tile = TMEM lane
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-            constexpr int ACC_PER_SB = TC_SB_TARGETS / TC_N;
-            constexpr int WPA = TC_N / 32;                         // packed words per accumulator and row
-            TCLOG("job start", job_id, n_sb);
-            for (int sb = 0; sb < n_sb; ++sb) {
-                const uint32_t sbi = sb_it + sb, pb = sbi & 1;
-                mbar_wait(&S.cm_empty[pb], (uint32_t)(((sbi >> 1) & 1) ^ 1));   // the exact warps have read this buffer
-                uint32_t* out = S.cm[pb] + row;
-#pragma unroll
-                for (int a = 0; a < ACC_PER_SB; ++a) {
-                    const uint32_t ai = acc_it + (uint32_t)(sb * ACC_PER_SB + a), buf = ai % TC_NBUF;
-#if SPK_SPIN >= 2
-                    mbar_wait_spin(&S.tmem_full[buf], (ai / TC_NBUF) & 1);
-#else
-                    mbar_wait(&S.tmem_full[buf], (ai / TC_NBUF) & 1);
-#endif
-                    if (a == 0) TCLOG(" sb first acc ready", sb, 0);
-                    if (warp == 2) TCLOGF("E full ok", ai, 0);
-                    tc_fence_after();
-                    const uint32_t ta = lane_addr + buf * TC_N;
-                    uint32_t wv[WPA][16];                          // WPA x 32 columns of fp16 accumulators, two per register
-#pragma unroll
-                    for (int g = 0; g < WPA; ++g) tmem_ld16p(ta + 32 * g, wv[g]);
-                    tmem_ld_wait();
-                    if (warp == 2) TCLOGF("E ld done", ai, 0);
-                    // the values are in registers: hand the accumulator back before reducing them
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&S.tmem_empty[buf]);
-                    if (warp == 2) TCLOGF("E arrived", ai, 0);
-#pragma unroll
-                    for (int g = 0; g < WPA; ++g) out[(WPA * a + g) * TC_TILE] = pmin16(wv[g]);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.cm_full[pb]);          // release: the warp's minima are visible to the exact warps
-                TCLOG(" sb min pass done", sb, 0);
-            }
-        } else {
-            // ===== exact warps (4): one thread per query row: filter the chunk minima, re-evaluate the survivors =====
-            const int q = warp & 3;
-            const int row = q * 32 + lane;                         // query row inside the tile
-            const int gq = job * TC_TILE + row;                    // query index inside the cloud
-            const bool live = gq < nq;
-            const float* Qx = (dir ? p.xyz2 : p.xyz1) + (size_t)b * nq * 3;
-            const float* Tx = (dir ? p.xyz1 : p.xyz2) + (size_t)b * nt * 3;
-            const ChamferMeta mt = p.meta[b];
-            const float tau = mt.tau, scale2 = mt.scale2, bias = mt.bias;
-            const bool eval_all = mt.nonfinite != 0.f;
-            float qx = 0.f, qy = 0.f, qz = 0.f;
-            if (live) { qx = __ldg(Qx + 3 * (size_t)gq); qy = __ldg(Qx + 3 * (size_t)gq + 1); qz = __ldg(Qx + 3 * (size_t)gq + 2); }
-            // reference: the first target initialises the running best (`k==0 || d<best`, chamfer.cu:36)
-            const int t_first = sb0 * TC_SB_TARGETS;                // first target of this (sub-)job: always a real point
-            const float t0x = __ldg(Tx + 3 * (size_t)t_first), t0y = __ldg(Tx + 3 * (size_t)t_first + 1), t0z = __ldg(Tx + 3 * (size_t)t_first + 2);
-            float best_d = 0.f;
-            int best_i = t_first;
-
-            for (int sb = 0; sb < n_sb; ++sb) {
-                const uint32_t sbi = sb_it + sb, pb = sbi & 1;
-                constexpr int NW = TC_CM_WORDS;                             // 32 words = 64 chunk minima per row
-                uint32_t cm[NW];
-                mbar_wait(&S.cm_full[pb], (uint32_t)((sbi >> 1) & 1));
-                {
-                    const uint32_t* in = S.cm[pb] + row;
-#pragma unroll
-                    for (int i = 0; i < NW; ++i) cm[i] = in[i * TC_TILE];
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.cm_empty[pb]);             // in registers: the buffer may be refilled
-                // ---- filter: chunks whose minimum is within the error slack of the row minimum (or of the
-                // exact best so far).  Everything is a positive fp16 pattern: 15-bit unsigned compares.
-                uint32_t rm = __vimin3_u16x2(cm[0], cm[1], cm[2]);
-#pragma unroll
-                for (int i = 3; i + 1 < NW; i += 2) rm = __vimin3_u16x2(rm, cm[i], cm[i + 1]);
-                rm = __vminu2(rm, cm[NW - 1]);
-                const uint32_t r16 = min(rm & 0xFFFFu, rm >> 16);
-                if (sb == 0) best_d = ref_sqdist_tc(qx, qy, qz, t0x, t0y, t0z);
-                // threshold: min(row minimum, exact best) widened by the fp16 rounding of the accumulator
-                // (relative, 2^-8 = 4 ulp) and the error bound of the operands (absolute, tau), rounded UP to fp16
-                float thr = fminf(__half2float(__ushort_as_half((unsigned short)r16)), fmaf(best_d, scale2, bias));
-                thr = fmaf(thr, 1.00390625f, tau);
-                uint32_t t16 = (uint32_t)__half_as_ushort(__float2half_ru(thr));
-                if (!(thr == thr) || t16 > 0x7FFFu) t16 = 0x7FFFu;       // NaN / negative garbage: evaluate everything
-                // mask bit i (i < 16): chunk in the low lane of word i, bit 16+i: its high lane; words 16..31 in the upper half
-                uint32_t m_lo = 0, m_hi = 0;
-                if (eval_all) {
-                    m_lo = m_hi = 0xFFFFFFFFu;
-                } else {
-                    // per lane (0x8000 | t) - c keeps bit 15 exactly when c <= t (both are 15-bit values: no borrow
-                    // crosses the lanes); the bits 15 / 31 of word i go to mask bits i / 16+i
-                    const uint32_t T2 = (t16 * 0x10001u) | 0x80008000u;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        m_lo |= ((T2 - cm[i]) >> (15 - i)) & (0x10001u << i);
-                        m_hi |= ((T2 - cm[16 + i]) >> (15 - i)) & (0x10001u << i);
-                    }
-                }
-                unsigned long long mask = live ? (((unsigned long long)m_hi << 32) | m_lo) : 0ull;
-#ifdef SPK_TIMING
-                atomicAdd(&S.dbg[0], __popcll(mask)); atomicAdd(&S.dbg[1], live ? 1 : 0);
-#endif
-                // ---- exact float32 re-evaluation of the surviving chunks (reference expression) ----
-                const uint32_t tb = sbi % TC_T4_BUFS;
-                mbar_wait(&S.t4_full[tb], (uint32_t)((sbi / TC_T4_BUFS) & 1));
-                const float4* tsm = S.t4[tb];
-                TCLOG(" sb filter done, t4 ready", sb, __popcll(mask));
-                const int sb_base = (sb0 + sb) * TC_SB_TARGETS;
-                while (mask) {
-                    const int pbit = __ffsll((long long)mask) - 1;
-                    mask &= mask - 1;
-                    // word w -> accumulator w / 4, 32-column group w % 4; the high lane holds the odd columns = targets 16..31
-                    const int w = ((pbit >> 5) << 4) | (pbit & 15), hi = (pbit >> 4) & 1;
-                    const int l0 = w * 32 + hi * TC_CHUNK;                  // inside the super-block
-                    // every chunk starts on a 256-byte boundary: rotate the visiting order by the lane so
-                    // that the 8 lanes of a quarter-warp hit 8 different bank groups (no LDS.128 conflicts).
-                    // All 16 exact distances first (FMA pipe), then ONE min tree and the lowest offset that
-                    // attains it -- 2.5 ALU instructions per target instead of a compare/select chain.
-                    float dv[TC_CHUNK];
-                    int rj[TC_CHUNK];
-#pragma unroll
-                    for (int j = 0; j < TC_CHUNK; ++j) {
-                        rj[j] = (j + lane) & (TC_CHUNK - 1);
-                        const float4 tg = tsm[l0 + rj[j]];               // padding targets are +inf: never the minimum
-                        dv[j] = ref_sqdist_tc(qx, qy, qz, tg.x, tg.y, tg.z);
-                    }
-                    const float dmin = min16(dv);                        // NaN distances are skipped by min
-                    int rmin_off = 99;
-#pragma unroll
-                    for (int j = 0; j < TC_CHUNK; ++j) rmin_off = min(rmin_off, dv[j] == dmin ? rj[j] : 99);
-                    const int t = sb_base + l0 + rmin_off;
-                    // first minimum: smaller distance, or equal distance at a lower index
-                    if (rmin_off < TC_CHUNK && (dmin < best_d || (dmin == best_d && t < best_i))) { best_d = dmin; best_i = t; }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.t4_empty[tb]);
-                TCLOG(" sb exact done", sb, 0);
-            }
-            if (NS == 1 && p.loss != nullptr)
-                loss_contribute(p, b, dir, lane, live ? best_d : 0.f);
-            if (live) {
-                if (NS == 1) {
-                    ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = best_d;
-                    ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = best_i;
-                } else {
-                    // distances are >= +0: their bit patterns order like the values, the index breaks ties
-                    // downwards -> the 64-bit minimum over the sub-jobs IS the first minimum
-                    atomicMin((dir ? p.packed2 : p.packed1) + (size_t)b * nq + gq,
-                              ((unsigned long long)__float_as_uint(best_d) << 32) | (unsigned)best_i);
-                }
-            }
-            if (NS > 1) {
-                // the sub-job that arrives last at the query tile's counter unpacks the merged minima.
-                // Ordering: the barrier orders the threads' atomics before the elected thread's
-                // acq_rel increment (release, cumulative); the last arriver's increment acquires every
-                // earlier sub-job's minima, the second barrier hands that to its other threads.
-                exact_bar();
-                if (warp == 2 + TC_MIN_WARPS && lane == 0) {
-                    int* cnt = p.counters + (size_t)b * (p.tiles1 + p.tiles2) + (dir ? p.tiles1 : 0) + job;
-                    int old;
-                    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(cnt) : "memory");
-                    S.last = (old == NS - 1);
-                }
-                exact_bar();
-                float merged = 0.f;
-                if (S.last && live) {
-                    unsigned long long v;
-                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"((dir ? p.packed2 : p.packed1) + (size_t)b * nq + gq) : "memory");
-                    merged = __uint_as_float((unsigned)(v >> 32));
-                    ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = merged;
-                    ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = (int)(unsigned)v;
-                }
-                if (S.last && p.loss != nullptr)                   // exactly one sub-job per query tile gets here
-                    loss_contribute(p, b, dir, lane, merged);
-                exact_bar();                                       // S.last is rewritten by the next split job
-            }
-        }
-        if (warp >= 2) TCLOG("job end", job_id, 0);
-        ring_it += (uint32_t)T; acc_it += (uint32_t)(TC_TILE / TC_N) * (uint32_t)T; sb_it += (uint32_t)n_sb;
+    // producer state (thread 0 only): the step whose operand loads / MMA are issued next
+    int ld_job = blockIdx.x, ld_pass = 0; uint32_t ld_step = 0, ld_jobn = 0; bool ld_valid = ld_job < total_jobs;
+    int mm_job = blockIdx.x, mm_pass = 0; uint32_t mm_step = 0, mm_jobn = 0; bool mm_valid = mm_job < total_jobs;
+    if (tid == 0 && ld_valid) {
+        issue_targets(ld_job, 0);
+        issue_loads(ld_job, ld_pass, ld_step, ld_jobn);
+        ld_valid = next_step(ld_job, ld_pass, ld_jobn); ++ld_step;
+        if (ld_valid && ld_pass != 0) { issue_loads(ld_job, ld_pass, ld_step, ld_jobn); ld_valid = next_step(ld_job, ld_pass, ld_jobn); ++ld_step; }
+        issue_mma(mm_step, mm_jobn, true);
+        mm_valid = next_step(mm_job, mm_pass, mm_jobn); ++mm_step;
     }
 
-#ifdef SPK_TIMING
-    __syncthreads();
-    if (tid == 0 && blockIdx.x == 0) for (int i = 0; i < min(tlog_n, 320); ++i) printf("  t=%7lld %s %d %d\n", tlog_t[i], tlog_s[i], tlog_a[i], tlog_b[i]);
-    if (tid == 0 && blockIdx.x < 2) printf("tc cta %d: chunks evaluated %d over %d (row, half, super-block) filters = %.3f each\n", blockIdx.x, S.dbg[0], S.dbg[1], (float)S.dbg[0] / (float)max(S.dbg[1], 1));
-#endif
+    uint32_t step = 0, cur_jobn = 0;
+    for (int job_id = blockIdx.x; job_id < total_jobs; job_id += gridDim.x, ++cur_jobn) {
+        int b, dir, tile; decode(job_id, b, dir, tile);
+        const int tgt = 1 - dir;
+        const int nq = p.n[dir], nt = p.n[tgt];
+        const int passes = p.nc_pad[tgt] / TC_NC, nc_t = p.nc[tgt];
+        const ChamferMeta mt = p.meta[b];
+        const bool eval_all = mt.nonfinite != 0.f;
+        const float* Tx = p.xyz[tgt] + (size_t)b * nt * 3;
+        const int row = tile * TC_TILE + tid;                       // position in the SORTED query cloud
+        // query: sorted order (neighbouring lanes are neighbouring points); non-finite samples are not sorted
+        float qx = 0.f, qy = 0.f, qz = 0.f; int qorig = row;
+        const bool live = row < nq;
+        if (live) {
+            if (eval_all) {
+                const float* q = p.xyz[dir] + ((size_t)b * nq + row) * 3;
+                qx = __ldg(q); qy = __ldg(q + 1); qz = __ldg(q + 2);
+            } else {
+                const float4 q = __ldg(p.S[dir] + (size_t)b * p.nc_pad[dir] * TC_CHUNK + row);
+                qx = q.x; qy = q.y; qz = q.z; qorig = __float_as_int(q.w);
+            }
+        }
+        // reference: the first target initialises the running best (`k==0 || d<best`, chamfer.cu:36)
+        float best_d = ref_sqdist_tc(qx, qy, qz, __ldg(Tx), __ldg(Tx + 1), __ldg(Tx + 2));
+        int best_i = 0;
+        if (eval_all && live) ref_order_nn(Tx, nt, qx, qy, qz, best_d, best_i);
+        // first minimum: smaller distance, or equal distance at a lower original index
+        auto take = [&](float dmin, int imin) { if (dmin < best_d || (dmin == best_d && imin < best_i)) { best_d = dmin; best_i = imin; } };
+        float tbias = 0.f;                                          // bias of the target cloud's chunk rows
+        int home = 0;                                               // chunk of the query's own cell in the target cloud's grid
+        if (!eval_all && live) {
+            const ChamferGrid gi = p.grid[tgt][b];
+            const uint32_t code = hilbert_code((uint32_t)cell_of(qx, gi.lo[0], gi.inv[0]), (uint32_t)cell_of(qy, gi.lo[1], gi.inv[1]), (uint32_t)cell_of(qz, gi.lo[2], gi.inv[2]));
+            tbias = gi.bias;
+            home = min((int)__ldg(p.cellstart[tgt] + (size_t)b * SORT_CELLS + code), nt - 1) >> 4;
+            if (passes > 1) {
+                // a good first bound before the first pass: the points around the query's own cell (global memory; with one
+                // pass the whole cloud is in shared memory and the home chunk is evaluated from there)
+                const float4* tg = p.S[tgt] + (size_t)b * p.nc_pad[tgt] * TC_CHUNK + (size_t)home * TC_CHUNK;
+                float dv[TC_CHUNK];
+#pragma unroll
+                for (int k = 0; k < TC_CHUNK; ++k) { const float4 t = __ldg(tg + k); dv[k] = ref_sqdist_tc(qx, qy, qz, t.x, t.y, t.z); }
+                const float dmin = min16(dv);
+                int imin = 0x7FFFFFFF;
+#pragma unroll
+                for (int k = 0; k < TC_CHUNK; ++k) imin = min(imin, dv[k] == dmin ? __float_as_int(__ldg(&tg[k].w)) : 0x7FFFFFFF);
+                take(dmin, imin);
+            }
+        }
+        // the 16 points of chunk jl of the pass (shared memory) against query (x, y, z): minimum distance and the lowest original
+        // index that attains it.  Every chunk starts on a 256-byte boundary: the visiting order is XOR-swizzled by the lane so that
+        // the lanes of a quarter-warp hit different banks (one LOP3 per address).
+        auto chunk_min = [&](int jl, float x, float y, float z, float bound, float& dmin, int& imin) {
+            const uint32_t base = smem_u32(S.tgt + jl * TC_CHUNK) | ((uint32_t)(lane & 15) << 4);
+            float dv[TC_CHUNK];
+#pragma unroll
+            for (int k = 0; k < TC_CHUNK; ++k) {
+                float tx, ty, tz, tw;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tx), "=f"(ty), "=f"(tz), "=f"(tw) : "r"(base ^ (uint32_t)(k << 4)));
+                dv[k] = ref_sqdist_tc(x, y, z, tx, ty, tz);          // padding points are +inf: never the minimum
+            }
+            dmin = min16(dv);
+            imin = 0x7FFFFFFF;
+            if (dmin <= bound) {
+                // which points attain the minimum: almost always one -> one more shared-memory read for its original index
+                uint32_t eq = 0;
+#pragma unroll
+                for (int k = 0; k < TC_CHUNK; ++k) eq |= (dv[k] == dmin) ? (1u << k) : 0u;
+                while (eq) {
+                    const int k = __ffs((int)eq) - 1;
+                    eq &= eq - 1;
+                    int iw;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(iw) : "r"((base ^ (uint32_t)(k << 4)) + 12u));
+                    imin = min(imin, iw);
+                }
+            }
+            TC_COUNT(4, 1);
+        };
+        // a queued candidate (it passed the box test of its query): the chunk's points; the result merges through a 64-bit
+        // shared-memory minimum -- distances are >= +0, so their bit patterns order like the values and the index breaks ties
+        auto run_item = [&](uint32_t item) {
+            const int r = (int)(item >> 7), jl = (int)(item & 127u);
+            const float4 q = S.q4[r];
+            const float bd = __uint_as_float((uint32_t)(S.best[r] >> 32));
+            float dmin; int imin;
+            chunk_min(jl, q.x, q.y, q.z, bd, dmin, imin);
+            if (dmin <= bd) atomicMin(&S.best[r], ((unsigned long long)__float_as_uint(dmin) << 32) | (unsigned)imin);
+        };
+
+        for (int pass = 0; pass < passes; ++pass, ++step) {
+            uint32_t w[64];                                        // 128 fp16 values V_j, two per register
+            mbar_wait(&S.mma_done, step & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tmem_ld16p(lane_addr + 32 * g, w + 16 * g);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_wait(&S.t_full, step & 1);                        // this pass's boxes and targets have landed
+            {   // this pass's capped chunks (one flag per thread -> four ballot words)
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, S.box[2 * tid].w != 0.f);
+                if (lane == 0) S.big[warp] = bal;
+            }
+            if (tid == 0) S.qn = 0;
+            __syncthreads();                                       // accumulator in registers everywhere: TMEM and the operand stages are free
+            // Producer (thread 0).  Operand loads run up to two steps ahead, but the single query-tile buffer may only be
+            // refilled once this job's last MMA (the one just drained) is done; the next job's first MMA is then issued
+            // after the enqueue phase below, when that tile has had time to land.
+            bool mma_late = false;
+            if (tid == 0) {
+                if (mm_valid) { if (mm_pass != 0) { issue_mma(mm_step, mm_jobn, false); mm_valid = next_step(mm_job, mm_pass, mm_jobn); ++mm_step; } else mma_late = true; }
+                while (ld_valid && ld_step <= step + 2 && (ld_pass != 0 || (pass == passes - 1 && ld_jobn == cur_jobn + 1))) {
+                    issue_loads(ld_job, ld_pass, ld_step, ld_jobn); ld_valid = next_step(ld_job, ld_pass, ld_jobn); ++ld_step;
+                }
+            }
+            const bool act = !eval_all && live;
+            uint32_t over[4] = {0u, 0u, 0u, 0u};
+            if (act) {
+                if (passes == 1) {                                   // a good first bound: the points around the query's own cell
+                    float dmin; int imin;
+                    chunk_min(home, qx, qy, qz, best_d, dmin, imin);
+                    if (dmin <= best_d) take(dmin, imin);
+                }
+                S.q4[tid] = make_float4(qx, qy, qz, 0.f);
+                S.best[tid] = ((unsigned long long)__float_as_uint(best_d) << 32) | (unsigned)best_i;
+                // ---- filter: V_j <= bias + 3 * scale2 * best (necessary for chunk j to hold a nearer point), plus slack ----
+                float t = fmaf(3.f * mt.scale2, best_d, tbias);
+                t = fmaf(t, 1.00390625f, mt.tau);
+                uint32_t t16 = (uint32_t)__half_as_ushort(__float2half_ru(t));
+                if (!(t == t) || t16 > 0x7C00u) t16 = 0x7C00u;       // NaN / garbage: everything passes
+                uint32_t m[4];
+                build_mask(w, t16, m);
+                TC_COUNT(0, 1); TC_COUNT(2, __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]));
+                // ---- candidates -> queue (a thread whose candidates do not fit evaluates them itself, after the barrier) ----
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t mm = m[g] | S.big[g];
+                    if (pass == passes - 1) {                        // chunks past the cloud's end (only reachable when best is +inf)
+                        const int lim = nc_t - pass * TC_NC - g * 32;
+                        mm &= lim >= 32 ? 0xFFFFFFFFu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+                    }
+                    // box test (float32, this query's best so far); survivors go to the queue
+                    uint32_t pass_bits = 0;
+                    while (mm) {
+                        const int bit = __ffs((int)mm) - 1;
+                        mm &= mm - 1;
+                        const int jl = g * 32 + bit;
+                        const float4 lo = S.box[2 * jl], hi = S.box[2 * jl + 1];
+                        const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.f), dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.f),
+                                    dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.f);
+                        const float d2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+                        TC_COUNT(3, 1);
+                        if (d2 * 0.999999f <= best_d) pass_bits |= 1u << bit;
+                    }
+                    const int cnt = __popc(pass_bits);
+                    uint32_t pos = cnt ? atomicAdd(&S.qn, (uint32_t)cnt) : 0u;
+                    while (pass_bits) {
+                        const int bit = __ffs((int)pass_bits) - 1;
+                        if (pos >= (uint32_t)TC_QCAP) { over[g] = pass_bits; break; }
+                        pass_bits &= pass_bits - 1;
+                        S.queue[pos++] = (uint16_t)((tid << 7) | (g * 32 + bit));
+                    }
+                }
+            }
+            if (mma_late) { issue_mma(mm_step, mm_jobn, true); mm_valid = next_step(mm_job, mm_pass, mm_jobn); ++mm_step; }
+            __syncthreads();
+            if (!eval_all) {
+                // ---- every thread takes queued candidates round-robin: balanced whatever the per-query counts are ----
+                const uint32_t total = min(S.qn, (uint32_t)TC_QCAP);
+                for (uint32_t it = tid; it < total; it += TC_THREADS) run_item(S.queue[it]);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t mm = over[g];
+                    while (mm) { const int bit = __ffs((int)mm) - 1; mm &= mm - 1; run_item((uint32_t)((tid << 7) | (g * 32 + bit))); }
+                }
+            }
+            __syncthreads();                                       // every thread is done with this pass's boxes / targets / queue
+            if (act) {
+                const unsigned long long v = S.best[tid];
+                best_d = __uint_as_float((uint32_t)(v >> 32)); best_i = (int)(uint32_t)v;
+            }
+            if (tid == 0) {
+                int nj = job_id, np_ = pass; uint32_t dummy = 0;
+                if (next_step(nj, np_, dummy)) issue_targets(nj, np_);
+            }
+        }
+        if (p.loss != nullptr) {
+            float v = live ? best_d : 0.f;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+            if (lane == 0) atomicAdd(p.loss + b, v / (float)nq);
+        }
+        if (live) {
+            p.dist[dir][(size_t)b * nq + qorig] = best_d;
+            p.idx[dir][(size_t)b * nq + qorig] = best_i;
+        }
+    }
     pdl_tail_trigger();
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_NC));
     }
 }
 
 // host-side entry used by chamfer.cu -----------------------------------------------------------
-static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-size_t chamfer_tc_workspace_bytes(int B, int n, int m) {
-    const size_t n_pad = round_up(n, TC_SB_TARGETS), m_pad = round_up(m, TC_SB_TARGETS);
-    const size_t tiles = (size_t)(n + TC_TILE - 1) / TC_TILE + (size_t)(m + TC_TILE - 1) / TC_TILE;
-    return 2 * (size_t)B * (n_pad + m_pad) * 32 + (size_t)B * (n_pad + m_pad) * 16 +
-           (((size_t)B * sizeof(ChamferMeta) + 255) & ~(size_t)255) + 256 +
-           (size_t)B * ((size_t)n + m) * 8 + ((((size_t)B * tiles * 4) + 255) & ~(size_t)255) + 256;    // split-job merge
+struct TcLayout {
+    int n_pad[2], nc[2], nc_pad[2];
+    size_t off_meta, off_S[2], off_A[2], off_Bc[2], off_box[2], off_cs[2], off_grid[2], total;
+};
+static TcLayout tc_layout(int B, int n, int m) {
+    TcLayout L;
+    const int cnt[2] = {n, m};
+    size_t o = 0;
+    L.off_meta = o; o += round_up((size_t)B * sizeof(ChamferMeta), 256);
+    for (int c = 0; c < 2; ++c) {
+        L.n_pad[c] = (int)round_up((size_t)cnt[c], TC_TILE);
+        L.nc[c] = (cnt[c] + TC_CHUNK - 1) / TC_CHUNK;
+        L.nc_pad[c] = (int)round_up((size_t)L.nc[c], TC_NC);
+        L.off_S[c] = o; o += round_up((size_t)B * L.nc_pad[c] * TC_CHUNK * 16, 256);     // whole passes: a pass is one bulk copy
+        L.off_A[c] = o; o += round_up((size_t)B * L.n_pad[c] * 32, 256);
+        L.off_Bc[c] = o; o += round_up((size_t)B * L.nc_pad[c] * 32, 256);
+        L.off_box[c] = o; o += round_up((size_t)B * L.nc_pad[c] * 32, 256);
+        L.off_cs[c] = o; o += round_up((size_t)B * SORT_CELLS * 2, 256);
+        L.off_grid[c] = o; o += round_up((size_t)B * sizeof(ChamferGrid), 256);
+    }
+    L.total = o + 256;                    // + alignment of the caller's pointer
+    return L;
 }
+
+bool chamfer_tc_supported(int n, int m) { return n >= 1 && m >= 1 && n <= TC_MAX_POINTS && m <= TC_MAX_POINTS; }
+
+size_t chamfer_tc_workspace_bytes(int B, int n, int m) { return tc_layout(B, n, m).total; }
 
 int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
                        float* dist2, int32_t* idx1, int32_t* idx2, float* loss, void* ws, size_t ws_bytes,
                        cudaStream_t st) {
-    if (ws_bytes < chamfer_tc_workspace_bytes(B, n, m) || ws == nullptr)
-        return fail(SPK_E_WORKSPACE, "chamfer_fwd_f32: workspace of %zu bytes needed, %zu given", chamfer_tc_workspace_bytes(B, n, m), ws_bytes);
+    const TcLayout L = tc_layout(B, n, m);
+    if (ws_bytes < L.total || ws == nullptr)
+        return fail(SPK_E_WORKSPACE, "chamfer_fwd_f32: workspace of %zu bytes needed, %zu given", L.total, ws_bytes);
     if (((uintptr_t)ws & 15) != 0) return fail(SPK_E_ALIGN, "chamfer_fwd_f32: workspace must be 16-byte aligned");
-    // rows are padded to whole super-blocks so that the target loop has no ragged tail
-    const int n_pad = round_up(n, TC_SB_TARGETS), m_pad = round_up(m, TC_SB_TARGETS);
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-    PrepParams pp;
-    pp.xyz1 = xyz1; pp.xyz2 = xyz2; pp.n = n; pp.m = m; pp.n_pad = n_pad; pp.m_pad = m_pad;
-    pp.meta = reinterpret_cast<ChamferMeta*>(base);
-    unsigned char* ops = base + (((size_t)B * sizeof(ChamferMeta) + 255) & ~(size_t)255);
-    pp.A1 = ops; pp.B1 = pp.A1 + (size_t)B * n_pad * 32;
-    pp.A2 = pp.B1 + (size_t)B * n_pad * 32; pp.B2 = pp.A2 + (size_t)B * m_pad * 32;
-    pp.T1 = reinterpret_cast<float4*>(pp.B2 + (size_t)B * m_pad * 32); pp.T2 = pp.T1 + (size_t)B * n_pad;
-    // Fewer jobs than persistent CTAs (small batches: B=1 validation clouds): the target range of every
-    // query tile is split into sub-jobs that merge through a 64-bit atomicMin; the last one to arrive
-    // unpacks.  A sub-job costs ~1.5 us of merge on top of ~3 us per super-block (measured), so splitting
-    // only pays when the grid is underfilled; the split minimising the makespan estimate wins.
-    // (Splitting to even out the tail of config A -- 3.46 jobs per CTA -- was measured SLOWER: 45.8 vs 33.4 us.)
-    const int tiles1 = (n + TC_TILE - 1) / TC_TILE, tiles2 = (m + TC_TILE - 1) / TC_TILE;
-    const long long ctas = 2LL * sm_count();
-    const long long jobs1 = (long long)(tiles1 + tiles2) * B;
-    int split = 1;
-    if (jobs1 < ctas) {
-        const double sb_avg = 0.5 * (n_pad + m_pad) / TC_SB_TARGETS;          // super-blocks per unsplit job
-        double best = 1e30;
-        for (int c = 1; c <= 8; c *= 2) {
-            const double waves = (double)((jobs1 * c + ctas - 1) / ctas);
-            const double cost = waves * (3.0 * sb_avg / c + (c > 1 ? 1.5 : 0.0));
-            if (cost < best - 1e-9) { best = cost; split = c; }
-        }
+    SortParams sp;
+    SearchParams qp;
+    const float* xyz[2] = {xyz1, xyz2};
+    const int cnt[2] = {n, m};
+    for (int c = 0; c < 2; ++c) {
+        sp.xyz[c] = xyz[c]; sp.n[c] = cnt[c]; sp.n_pad[c] = L.n_pad[c]; sp.nc[c] = L.nc[c]; sp.nc_pad[c] = L.nc_pad[c];
+        sp.S[c] = reinterpret_cast<float4*>(base + L.off_S[c]);
+        sp.A[c] = base + L.off_A[c]; sp.Bc[c] = base + L.off_Bc[c];
+        sp.box[c] = reinterpret_cast<float4*>(base + L.off_box[c]);
+        sp.cellstart[c] = reinterpret_cast<uint16_t*>(base + L.off_cs[c]);
+        sp.grid[c] = reinterpret_cast<ChamferGrid*>(base + L.off_grid[c]);
+        qp.xyz[c] = xyz[c]; qp.n[c] = cnt[c]; qp.n_pad[c] = L.n_pad[c]; qp.nc[c] = L.nc[c]; qp.nc_pad[c] = L.nc_pad[c];
+        qp.S[c] = sp.S[c]; qp.A[c] = sp.A[c]; qp.Bc[c] = sp.Bc[c]; qp.box[c] = sp.box[c];
+        qp.cellstart[c] = sp.cellstart[c]; qp.grid[c] = sp.grid[c];
+        qp.tiles[c] = (cnt[c] + TC_TILE - 1) / TC_TILE;
     }
-    if (const char* e = getenv("SPK_TC_SPLIT")) split = std::max(1, std::min(64, atoi(e)));
-    const int S1 = std::max(1, std::min(split, m_pad / TC_SB_TARGETS));    // direction 0 scans xyz2
-    const int S2 = std::max(1, std::min(split, n_pad / TC_SB_TARGETS));
-    pp.packed1 = nullptr; pp.packed2 = nullptr; pp.counters = nullptr; pp.n_counters = tiles1 + tiles2;
-    if (S1 > 1 || S2 > 1) {
-        unsigned char* q = reinterpret_cast<unsigned char*>(pp.T2 + (size_t)B * m_pad);
-        q = reinterpret_cast<unsigned char*>(((uintptr_t)q + 255) & ~(uintptr_t)255);
-        pp.packed1 = reinterpret_cast<unsigned long long*>(q);
-        pp.packed2 = pp.packed1 + (size_t)B * n;
-        pp.counters = reinterpret_cast<int*>(pp.packed2 + (size_t)B * m);
-    }
-    pp.loss = loss;
-    const int slices = std::max(1, std::min(16, (n_pad + m_pad) / 512));
-    SPK_CUDA(launch_k(chamfer_prep_kernel, dim3(slices, B), dim3(256), 0, st, pp));
+    sp.meta = reinterpret_cast<ChamferMeta*>(base + L.off_meta); sp.loss = loss;
+    qp.meta = sp.meta; qp.loss = loss; qp.B = B;
+    qp.dist[0] = dist1; qp.dist[1] = dist2; qp.idx[0] = idx1; qp.idx[1] = idx2;
 
-    TcParams tp;
-    tp.xyz1 = xyz1; tp.xyz2 = xyz2; tp.A1 = pp.A1; tp.B1 = pp.B1; tp.A2 = pp.A2; tp.B2 = pp.B2; tp.T1 = pp.T1; tp.T2 = pp.T2; tp.meta = pp.meta; tp.B = B;
-    tp.dist1 = dist1; tp.dist2 = dist2; tp.idx1 = idx1; tp.idx2 = idx2;
-    tp.n = n; tp.m = m; tp.n_pad = n_pad; tp.m_pad = m_pad;
-    tp.tiles1 = tiles1; tp.tiles2 = tiles2; tp.S1 = S1; tp.S2 = S2;
-    tp.packed1 = pp.packed1; tp.packed2 = pp.packed2; tp.counters = pp.counters;
-    tp.loss = loss;
-    // request enough shared memory that at most 2 CTAs share an SM (each owns 256 of the 512 TMEM columns)
-    const size_t smem = std::max(sizeof(TcSmem) + 128, (size_t)80 * 1024);
-    SPK_CUDA(cudaFuncSetAttribute(chamfer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long jobs = ((long long)tp.tiles1 * S1 + (long long)tp.tiles2 * S2) * B;
-    int grid = (int)std::min<long long>(jobs, 2LL * sm_count());         // persistent: 2 CTAs per SM
-    if (const char* e = getenv("SPK_TC_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
-    SPK_CUDA(launch_k(chamfer_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tp));
+    const int nmax = std::max(n, m);
+    size_t sort_smem = (size_t)SORT_CELLS * 4 + (size_t)((nmax + 3) & ~3) * 4 + (size_t)((nmax + 7) & ~7) * 2;
+    sp.stage = sort_smem + (size_t)nmax * 12 + 16 <= (size_t)200 * 1024;
+    if (sp.stage) sort_smem += (size_t)nmax * 12 + 16;
+    // function attributes are per device; set once per (device, size) -- benign race: every writer stores the same value
+    int dev = 0;
+    SPK_CUDA(cudaGetDevice(&dev));
+    static size_t sort_smem_set[64] = {0};
+    static bool search_attr[64] = {false};
+    const int dslot = (dev >= 0 && dev < 64) ? dev : 0;
+    if (sort_smem > sort_smem_set[dslot] || dev != dslot) {
+        SPK_CUDA(cudaFuncSetAttribute(chamfer_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+        sort_smem_set[dslot] = sort_smem;
+    }
+    SPK_CUDA(launch_k(chamfer_sort_kernel, dim3(2, B), dim3(SORT_THREADS), sort_smem, st, sp));
+
+    // dynamic shared memory sized so that at most 4 CTAs share an SM (each owns 128 of the 512 TMEM columns)
+    const size_t smem = std::max(sizeof(SearchSmem) + 128, (size_t)50 * 1024);
+    if (!search_attr[dslot] || dev != dslot) {
+        SPK_CUDA(cudaFuncSetAttribute(chamfer_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        search_attr[dslot] = true;
+    }
+    const long long jobs = (long long)(qp.tiles[0] + qp.tiles[1]) * B;
+    const int grid = (int)std::min<long long>(jobs, 4LL * sm_count());
+    SPK_CUDA(launch_k(chamfer_search_kernel, dim3(grid), dim3(TC_THREADS), smem, st, qp));
     return SPK_OK;
 }
 
 }  // namespace spk
+
+#ifdef SPK_TIMING
+extern "C" void spk_debug_tc_counters(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, spk::g_tc_dbg, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(spk::g_tc_dbg, z, sizeof(z)); }
+}
+#endif

@@ -14,6 +14,17 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.fixture(autouse=True, params=["auto", "dense", "sorted"])
+def chamfer_path(request, monkeypatch):
+    """Every test of this file runs three times: the library's own choice of forward kernel, the dense tensor-core
+    kernel (chamfer_dense.cu) forced, and the sorted search (chamfer_tc.cu) forced -- all must be bit-identical."""
+    if request.param != "auto":
+        monkeypatch.setenv("SPK_CHAMFER_PATH", request.param)
+    else:
+        monkeypatch.delenv("SPK_CHAMFER_PATH", raising=False)
+    return request.param
+
+
 def dev():
     return torch.device("cuda:0")
 
