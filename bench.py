@@ -1,22 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- SoftPool + Chamfer fwd+bwd throughput (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload A|A1|N8192]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload A|A1|N1024|N4096|N8192|N16384|C32..C512]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One STEP = one pass of the hot path over one batch of B synthetic clouds (per GPU):
   sp_topk_f32 -> sp_gather_fwd_f32 -> sp_gather_bwd_f32          (SoftPool fwd+bwd, keys given)
   chamfer_fwd_loss_f32 -> chamfer_bwd_f32                          (Chamfer fwd + mean loss + bwd, n = m = N)
-`value` = whole-job Mpoints/s = (n_gpus * B * N points) / (max-over-ranks step time), inputs
-resident in HBM, the step replayed as a CUDA graph, inputs rotating over several buffer sets whose
-footprint exceeds the 126 MB L2.  `e2e` = same step through the public Python API with HOST
-(pinned) inputs, H2D/D2H copies inside the timed region (step i+1's H2D runs on a copy stream under step
-i's kernels).  `roofline` = dominant call, timed live with CUDA events around CUDA-graph replays of that call
-alone over the rotating buffer sets (its inputs are never L2-resident); `roofline_softpool` / `roofline_chamfer`
-carry both groups.  `chains_overlapped` (informational) = the same step with the SoftPool chain and the Chamfer
-chain as two branches of one graph.  `cpu_baseline` = the CPU
-port of the reference path (oracle/softpool_torch_port.py + oracle/chamfer_oracle.c) on this host.
-Prints ONE JSON line on rank 0.
+`value` = whole-job Mpoints/s = (n_gpus * B * N points) / (max-over-ranks step time), inputs resident in HBM;
+the timed region is ONE CUDA-graph launch holding all `steps` steps (no host work inside the window), inputs rotating
+over several buffer sets whose footprint exceeds the 126 MB L2.  `e2e` = same step through the public Python API with
+HOST (pinned) inputs, H2D of every input and D2H of EVERY output inside the timed region (step i+1's H2D runs on a
+copy stream under step i's kernels).  `roofline` = dominant call, timed live with CUDA events around CUDA-graph
+replays of that call alone over the rotating buffer sets; `roofline_softpool` / `roofline_chamfer` carry both groups.
+`ref_gpu` (rank 0, outside the timed region) = the kernels to beat on the same GPU: the reference's own chamfer.cu
+compiled unmodified for sm_100 (oracle/_ref) and the reference SoftPool module (staged softpool.py, else the torch
+port) on CUDA tensors.  `cpu_baseline` / `--impl reference` = the reference path on this host's CPU cores: the
+reference SoftPool module itself (oracle/_ref/softpool_ref.py, `.cuda()` neutralised; kind "reference") when staged,
+else its op-for-op port, + the C restatement of chamfer.cu.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes
@@ -40,6 +41,20 @@ WORKLOADS = {
     "N8192": dict(B=32, C=256, N=8192, R=8, k=1024, cab=8,
                   name="SoftPool fwd+bwd (B=32,N=8192,C=256,R=8,k=1024,cab=8) + Chamfer (B=32, 8192<->8192)"),
 }
+# BASELINE config 5 (N sweep at the reference's sp_ratio = R = 8, i.e. k = N/8) and the C sweep of north_star (32 -> 512)
+for _n in (1024, 4096, 16384):
+    WORKLOADS["N%d" % _n] = dict(B=32, C=256, N=_n, R=8, k=_n // 8, cab=8,
+                                 name="SoftPool fwd+bwd (B=32,N=%d,C=256,R=8,k=%d,cab=8) + Chamfer (B=32, %d<->%d)" % (_n, _n // 8, _n, _n))
+for _c in (32, 64, 128, 512):
+    WORKLOADS["C%d" % _c] = dict(B=32, C=_c, N=2048, R=8, k=32, cab=8,
+                                 name="SoftPool fwd+bwd (B=32,N=2048,C=%d,R=8,k=32,cab=8) + Chamfer (B=32, 2048<->2048)" % _c)
+L2_NOTE = "b200 arm: inputs rotate over buffer sets of >= 400 MB (> 126 MB L2); reference arm: CPU, fresh pass per step"
+
+
+def config_of(w):
+    """Identical in both arms (the driver compares the `config` dicts of the two lines)."""
+    return {"workload": w["name"], "per_gpu_batch": w["B"], "points_per_cloud": w["N"], "l2": L2_NOTE}
+
 METRIC = "softpool_chamfer_fwd_bwd_throughput"
 UNIT = "Mpoints/s"
 K_PAD = 16     # MMA K of the tensor-core distance formulation (SURVEY 8d)
@@ -56,13 +71,17 @@ def load_peaks():
 
 def load_traffic(workload):
     """ncu-measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one
-    `ncu --set full` capture, profiles/r1_traffic.json, written by tools/ncu_traffic.py); {} when that
-    workload was not captured."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if not os.path.exists(p):
-        return {}
-    d = json.load(open(p)).get(workload, {})
-    return {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in d.items()}
+    `ncu --set full` capture, profiles/r2_traffic.json, written by tools/ncu_traffic.py); {} when that
+    workload was not captured.  CAVEAT: dram__bytes_write of a short kernel misses what the
+    write-back L2 has not evicted when the kernel ends (the backward's 67 MB grad_x showed as 10 MB), so the sum is
+    a LOWER bound for write-heavy kernels; `traffic_floor` = max(that, the kernel's own algorithmic write bytes)."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p)).get(workload, {})
+            if d:
+                return {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in d.items()}
+    return {}
 
 
 def traffic_of(traffic, *prefixes):
@@ -204,38 +223,27 @@ def run_b200(args, w, rank, local_rank, world):
     sets = [one] + [BufferSet(w, dev, 1235 + rank + 97 * i) for i in range(1, nsets)]
     B, N = w["B"], w["N"]
 
-    # ---- CUDA graphs: one per buffer set (single steps) + one holding a whole rotation of `nsets` steps, so that
-    # the timed loop pays one graph launch per rotation instead of one per step -------------------------------
+    # ---- ONE CUDA graph holds the whole timed region (`steps` steps rotating over the buffer sets), another the warm-up:
+    # between the two events there is a single graph launch and no host work at all -----------------------------------
     stream = torch.cuda.Stream(device=dev)
-    graphs = []
     with torch.cuda.stream(stream):
         for s in sets:
             step.run(s)                                            # warm (sets func attributes) before capture
         stream.synchronize()
-        for s in sets:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
-                step.run(s)
-            graphs.append(g)
-        rotation = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(rotation, stream=stream):
-            for s in sets:
-                step.run(s)
+        g_warm = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_warm, stream=stream):
+            for i in range(args.warmup):
+                step.run(sets[i % nsets])
+        g_timed = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_timed, stream=stream):
+            for i in range(args.steps):
+                step.run(sets[(args.warmup + i) % nsets])
     torch.cuda.synchronize(dev)
-
-    def replay_steps(k, start=0):
-        """k consecutive steps, buffer sets rotating from `start`: whole rotations as one graph launch each."""
-        i = 0
-        while i < k and (start + i) % nsets:                       # align to a rotation boundary
-            graphs[(start + i) % nsets].replay(); i += 1
-        while k - i >= nsets:
-            rotation.replay(); i += nsets
-        while i < k:
-            graphs[(start + i) % nsets].replay(); i += 1
 
     sampler = ClockSampler(local_rank)
     with torch.cuda.stream(stream):
-        replay_steps(args.warmup)
+        g_warm.replay()
+        g_timed.replay()            # untimed: the first replay of a graph also uploads it (measured: +8 us of launch gaps per step)
         stream.synchronize()
         spd.barrier()
         torch.cuda.synchronize(dev)
@@ -243,7 +251,7 @@ def run_b200(args, w, rank, local_rank, world):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
-        replay_steps(args.steps, start=args.warmup)
+        g_timed.replay()
         e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize(dev)
@@ -251,25 +259,25 @@ def run_b200(args, w, rank, local_rank, world):
         clocks = sampler.stop()
         spd.barrier()
     dev_ms = e0.elapsed_time(e1)
-    ms_per_step = spd.max_over_ranks(dev_ms, dev) / args.steps
+    per_rank = spd.gather_over_ranks(dev_ms / args.steps, dev)
+    ms_per_step = max(per_rank)
     points_per_step = spd.sum_over_ranks(B * N, dev)
     value = points_per_step / (ms_per_step * 1e-3) / 1e6
 
     # ---- informational: the SoftPool chain and the Chamfer chain are independent in this metric; captured as
-    # two branches of one CUDA graph they overlap (HBM-bound gather kernels next to the ALU-bound Chamfer
-    # kernel).  Reported beside `value`, never instead of it.
+    # two branches of one CUDA graph they overlap.  Reported beside `value`, never instead of it.
     overlap = None
     try:
         side = torch.cuda.Stream(device=dev)
-        graphs2 = []
+        n_o = min(args.steps, 60)
         with torch.cuda.stream(stream):
-            for s in sets:
-                g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2, stream=stream):
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, stream=stream):
+                for i in range(n_o):
                     fork, join = torch.cuda.Event(), torch.cuda.Event()
                     fork.record(stream)
                     side.wait_event(fork)
-                    cl = step.calls(s)
+                    cl = step.calls(sets[i % nsets])
                     with torch.cuda.stream(side):
                         for _, f in cl[N_SOFTPOOL_CALLS:]:
                             f()
@@ -277,23 +285,20 @@ def run_b200(args, w, rank, local_rank, world):
                     for _, f in cl[:N_SOFTPOOL_CALLS]:
                         f()
                     stream.wait_event(join)
-                graphs2.append(g2)
-            for i in range(args.warmup):
-                graphs2[i % nsets].replay()
+            g2.replay()
             stream.synchronize()
             o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             o0.record(stream)
-            for i in range(args.steps):
-                graphs2[i % nsets].replay()
+            g2.replay()
             o1.record(stream)
             stream.synchronize()
-        o_ms = spd.max_over_ranks(o0.elapsed_time(o1), dev) / args.steps
+        o_ms = spd.max_over_ranks(o0.elapsed_time(o1), dev) / n_o
         overlap = {"ms_per_step": o_ms, "value": points_per_step / (o_ms * 1e-3) / 1e6, "unit": UNIT,
                    "how": "same step, SoftPool chain and Chamfer chain as two branches of one CUDA graph"}
     except Exception as e:                      # informational leg: never fail the bench line
         overlap = {"error": repr(e)[:200]}
 
-    # ---- per-kernel device time: every C-ABI call captured alone in a CUDA graph (30 launches rotating
+    # ---- per-kernel device time: every C-ABI call captured alone in a CUDA graph (launches rotating
     # over the buffer sets, so its inputs are not L2-resident), CUDA events around 5 replays on `stream`
     kern_us = {}
     with torch.cuda.stream(stream):
@@ -316,53 +321,141 @@ def run_b200(args, w, rank, local_rank, world):
     fwd_b, bwd_b = algorithmic_bytes(w)
     traffic = load_traffic(args.workload)
     tr_sp = traffic_of(traffic, "sp_topk", "sp_gather_fwd", "sp_gather_bwd") if traffic else None
-    tr_ch = traffic_of(traffic, "chamfer_prep", "chamfer_tc") if traffic else None
+    tr_ch = traffic_of(traffic, "chamfer_") if traffic else None
     P = B * N * N
     sp_us = kern_us["sp_topk_f32"] + kern_us["sp_gather_fwd_f32"] + kern_us["sp_gather_bwd_f32"]
     ch_us = kern_us["chamfer_fwd_loss_f32"] + kern_us["chamfer_bwd_f32"]
     roof_sp = dict(bound="hbm", kernels="sp_topk_f32+sp_gather_fwd_f32+sp_gather_bwd_f32",
                    achieved=(fwd_b + bwd_b) / (sp_us * 1e-6) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
-                   algorithmic_bytes=fwd_b + bwd_b, us=sp_us, traffic=tr_sp, peak_source=peaks["source"])
+                   algorithmic_bytes=fwd_b + bwd_b, us=sp_us, traffic=tr_sp,
+                   traffic_note="ncu dram read+write of one capture; a LOWER bound for the write-heavy backward (write-back L2 not yet evicted at kernel end); steady state >= algorithmic write bytes",
+                   peak_source=peaks["source"])
     roof_sp["frac"] = roof_sp["achieved"] / roof_sp["peak"]
+    sorted_path = N * N >= 4096 * 4096 and B * 2 * N >= 65536     # chamfer.cu: chamfer_path()
     roof_ch = dict(bound="tensor", kernels="chamfer_fwd_loss_f32",
                    achieved=2.0 * P * K_PAD / (kern_us["chamfer_fwd_loss_f32"] * 1e-6) / 1e12, peak=peaks["bf16_tflops"],
-                   unit="TFLOP/s", issued_flops=2.0 * P * K_PAD, algorithmic_flops=8.0 * P,
+                   unit="TFLOP/s", counted_flops=2.0 * P * K_PAD, algorithmic_flops=8.0 * P,
                    direct_form_tflops=8.0 * P / (kern_us["chamfer_fwd_loss_f32"] * 1e-6) / 1e12,
                    us=kern_us["chamfer_fwd_loss_f32"], traffic=tr_ch, peak_source=peaks["source"],
-                   note="tcgen05 kind::f16 M=128 N=128 K=16 tiles, fp16 accumulators + exact fp32 refinement; achieved = 2*B*n*m*16 flops "
-                        "(each pair counted once, SURVEY 8d) / time of chamfer_fwd_loss_f32 (prep + tensor kernel, mean-loss folded in); both "
-                        "directions are issued, so the tensor pipe really executes twice that; the limiter is draining the accumulators "
-                        "from TMEM (~370 cycles per 128x128 tile and CTA), not the tensor pipe")
+                   path="sorted search (chamfer_tc.cu)" if sorted_path else "dense (chamfer_dense.cu)",
+                   note="achieved = 2*B*n*m*16 flops (the K=16 distance contraction, each pair counted once, SURVEY 8d) / time of "
+                        "chamfer_fwd_loss_f32 (prep + tensor kernel, mean loss folded in).  Dense path: every pair block is issued on "
+                        "tcgen05 (both directions: the pipe executes twice the counted flops); its ceiling is TMEM, not the tensor pipe: "
+                        "an accumulator column is held for the ~600-cycle MMA -> commit -> tcgen05.ld -> release round trip, so 512 columns x "
+                        "128 lanes cap an SM at ~110 pair distances per cycle (tools/micro/tc_pipe2_bench.cu, profiles/r2_tc_*.txt).  "
+                        "Sorted path: the pair block is NOT evaluated -- one MMA per 128 queries x 128 sixteen-point chunks filters, ~60 exact "
+                        "distances per query follow; `achieved` is then an equivalent rate, the tensor pipe itself is ~1 % busy")
     roof_ch["frac"] = roof_ch["achieved"] / roof_ch["peak"]
     dominant = roof_ch if kern_us["chamfer_fwd_loss_f32"] >= max(kern_us["sp_gather_fwd_f32"], kern_us["sp_gather_bwd_f32"]) else roof_sp
 
     # ---- e2e: public API, pinned host inputs, H2D + D2H inside the timed region -----------------------
     e2e = run_e2e(args, w, dev, stream, spd)
 
+    # ---- the kernels to beat on the same GPU (rank 0 only, outside every timed region) -----------------
+    ref_gpu = None
+    if rank == 0 and not args.no_ref_gpu:
+        try:
+            ref_gpu = run_ref_gpu(w, dev, kern_us)
+        except Exception as e:
+            ref_gpu = {"error": repr(e)[:300]}
+
     out = None
     if rank == 0:
+        srt = sorted(per_rank)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "per_gpu_batch": B, "points_per_step": int(points_per_step),
-                       "timing": "CUDA events around %d steps replayed from CUDA graphs (one launch per rotation of %d steps), max over ranks" % (args.steps, nsets),
-                       "l2": "inputs rotate over %d buffer sets (%.0f MB > 126 MB L2)" % (nsets, nsets * one.footprint() / 1e6),
-                       "wall_ms_per_step": wall_ms / args.steps, "parallelism": "batch-sharded, no data-path collective"},
+            "config": config_of(w),
+            "measurement": {"timing": "CUDA events around ONE CUDA-graph launch holding all %d steps (warm-up: a graph of %d steps, then one untimed replay of the timed graph), max over ranks" % (args.steps, args.warmup),
+                            "l2": "inputs rotate over %d buffer sets (%.0f MB > 126 MB L2)" % (nsets, nsets * one.footprint() / 1e6),
+                            "points_per_step": int(points_per_step), "wall_ms_per_step": wall_ms / args.steps,
+                            "ranks_ms_per_step": {"min": srt[0], "median": srt[len(srt) // 2], "max": srt[-1]},
+                            "parallelism": "batch-sharded, no data-path collective"},
             "roofline": dominant, "roofline_softpool": roof_sp, "roofline_chamfer": roof_ch,
             "kernel_us": kern_us, "softpool_fwd_bwd_us": sp_us, "chamfer_fwd_bwd_us": ch_us,
             "kernel_timing": "per C-ABI call: CUDA events around 5 replays of a CUDA graph holding %d launches that rotate over the %d buffer sets" % (reps, nsets),
-            "chains_overlapped": overlap,
+            "chains_overlapped": overlap, "ref_gpu": ref_gpu,
             "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "clocks": clocks,
         }
     return out
 
 
+def run_ref_gpu(w, dev, kern_us):
+    """The reference's own GPU code on this GPU: chamfer.cu compiled unmodified for sm_100 (oracle/_ref, built by
+    oracle/build_ref.py; it launches on the legacy default stream, chamfer.cu:142) and the reference SoftPool module
+    (staged softpool.py with the Sorter conv replaced by preset keys, else its op-for-op torch port) on CUDA tensors,
+    forward + autograd backward.  CUDA events on the default stream, after warm-up; per-call speed-ups beside them."""
+    import torch
+    from oracle import build_ref
+    B, C, N, R, k, cab = (w[x] for x in "B C N R k cab".split())
+    g = torch.Generator().manual_seed(5)
+    out = {"how": "reference chamfer.cu (unmodified, sm_100) + reference SoftPool module on CUDA tensors, CUDA events on the default stream, best of 3 x 5 calls"}
+    st = torch.cuda.default_stream(dev)
+
+    def timeit(fn, reps=5, rounds=3):
+        fn(); torch.cuda.synchronize(dev)
+        best = 1e30
+        for _ in range(rounds):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(reps):
+                fn()
+            e1.record(st)
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
+        return best
+
+    with torch.cuda.stream(st):
+        ref = build_ref.load_ref()
+        if ref is not None:
+            a = (torch.rand(B, N, 3, generator=g) - 0.5).to(dev); b = (torch.rand(B, N, 3, generator=g) - 0.5).to(dev)
+            d1 = torch.zeros(B, N, device=dev); d2 = torch.zeros(B, N, device=dev)
+            i1 = torch.zeros(B, N, dtype=torch.int32, device=dev); i2 = torch.zeros(B, N, dtype=torch.int32, device=dev)
+            g1 = torch.full((B, N), 1.0 / (N * B), device=dev)
+            gx1 = torch.zeros(B, N, 3, device=dev); gx2 = torch.zeros(B, N, 3, device=dev)
+            out["chamfer_fwd_us"] = timeit(lambda: ref.forward(a, b, d1, d2, i1, i2))
+
+            def bwd():
+                gx1.zero_(); gx2.zero_()                      # the reference accumulates into zeroed buffers (dist_chamfer.py:40-46)
+                ref.backward(a, b, gx1, gx2, g1, g1, i1, i2)
+            out["chamfer_bwd_us"] = timeit(bwd)
+            out["chamfer_speedup"] = {"fwd": out["chamfer_fwd_us"] / kern_us["chamfer_fwd_loss_f32"], "bwd": out["chamfer_bwd_us"] / kern_us["chamfer_bwd_f32"]}
+        else:
+            out["chamfer"] = "oracle/_ref not built"
+        x = torch.randn(B, C, N, generator=g).to(dev); keys = torch.randn(B, R, N, generator=g).to(dev)
+        gc = torch.randn(B, C, R, k, generator=g).to(dev); gb = torch.randn(B, C, R, cab, generator=g).to(dev)
+        mod = build_ref.load_ref_softpool(cpu=False)
+        if mod is not None:
+            class PresetKeys(torch.nn.Module):
+                def forward(self, _):
+                    return keys
+            sp = mod.SoftPool(regions=R, cabins=cab, sp_ratio=N // k, size_feat=C)
+            sp.sorter.conv1d = PresetKeys()
+            out["softpool_impl"] = "reference softpool.py (SoftPool.forward incl. its dead conv tail, Sorter conv -> preset keys)"
+
+            def sp_step():
+                xx = x.detach().requires_grad_(True)
+                sp_cube, sp_idx, cabins, id_activa = sp(xx)
+                torch.autograd.backward([sp_cube, cabins], [gc, gb])
+        else:
+            from oracle import softpool_torch_port as port
+            out["softpool_impl"] = "oracle/softpool_torch_port.py (op-for-op port of softpool.py:134-151) on CUDA tensors"
+
+            def sp_step():
+                port.forward_backward(x, keys, k, cab, gc, gb)
+        out["softpool_fwd_bwd_us"] = timeit(sp_step)
+        ours = kern_us["sp_topk_f32"] + kern_us["sp_gather_fwd_f32"] + kern_us["sp_gather_bwd_f32"]
+        out["softpool_speedup"] = out["softpool_fwd_bwd_us"] / ours
+    return out
+
+
 def run_e2e(args, w, dev, stream, spd):
     """Same step through the public Python API with HOST (pinned) inputs.  Every step copies all of its
-    inputs host->device and its results device->host inside the timed region.  The copies run on a copy
-    stream into one of two device input sets, so step i+1's H2D overlaps step i's kernels (what a user's
-    prefetching data loader does); events order copy -> compute -> reuse of the set."""
+    inputs host->device and EVERY result device->host inside the timed region (sp_cube, sp_idx, id_activa, cabins,
+    grad_x, dist1/2, idx1/2, loss, both Chamfer gradients).  The H2D copies run on a copy stream into one of two device
+    input sets, so step i+1's H2D overlaps step i's kernels (what a user's prefetching data loader does); events order
+    copy -> compute -> reuse of the set."""
     import torch
     import softpool_b200 as spb
     from softpool_b200 import ops
@@ -372,10 +465,14 @@ def run_e2e(args, w, dev, stream, spd):
     host = [pin(torch.randn(B, C, N, generator=g)), pin(torch.randn(B, R, N, generator=g)),
             pin(torch.randn(B, C, R, k, generator=g)), pin(torch.randn(B, C, R, cab, generator=g)),
             pin(torch.rand(B, N, 3, generator=g) - 0.5), pin(torch.rand(B, N, 3, generator=g) - 0.5)]
-    out_cab = pin(torch.empty(B, C, R, cab)); out_loss = pin(torch.empty(B)); out_g1 = pin(torch.empty(B, N, 3))
+    outs = dict(sp_cube=pin(torch.empty(B, C, R, k)), sp_idx=pin(torch.empty(B, R + 3, R, k)), id_activa=pin(torch.empty(B, N, dtype=torch.int64)),
+                cabins=pin(torch.empty(B, C, R, cab)), grad_x=pin(torch.empty(B, C, N)),
+                d1=pin(torch.empty(B, N)), d2=pin(torch.empty(B, N)), i1=pin(torch.empty(B, N, dtype=torch.int32)),
+                i2=pin(torch.empty(B, N, dtype=torch.int32)), loss=pin(torch.empty(B)),
+                g1=pin(torch.empty(B, N, 3)), g2=pin(torch.empty(B, N, 3)))
     cd = spb.chamferDist()
     h2d = sum(t.numel() * t.element_size() for t in host)
-    d2h = sum(t.numel() * t.element_size() for t in (out_cab, out_loss, out_g1))
+    d2h = sum(t.numel() * t.element_size() for t in outs.values())
     copy_stream = torch.cuda.Stream(device=dev)
     dsets = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]       # set j holds fresh inputs
@@ -393,15 +490,16 @@ def run_e2e(args, w, dev, stream, spd):
         dx, keys, gc, gb, a, b = dsets[j]
         x = dx.detach().requires_grad_(True)
         a = a.detach().requires_grad_(True)
+        b = b.detach().requires_grad_(True)
         idx, sp_idx, id_activa = ops.softpool_topk(keys, k)
         sp_cube, cabins = ops.softpool_gather(x, idx, cab)
         torch.autograd.backward([sp_cube, cabins], [gc, gb])
-        d1, d2, _, _ = cd(a, b)
+        d1, d2, i1, i2 = cd(a, b)
         loss = d1.mean(1) + d2.mean(1)
         loss.mean().backward()
-        out_cab.copy_(cabins.detach(), non_blocking=True)
-        out_loss.copy_(loss.detach(), non_blocking=True)
-        out_g1.copy_(a.grad, non_blocking=True)
+        for name, t in (("sp_cube", sp_cube), ("sp_idx", sp_idx), ("id_activa", id_activa), ("cabins", cabins), ("grad_x", x.grad),
+                        ("d1", d1), ("d2", d2), ("i1", i1), ("i2", i2), ("loss", loss), ("g1", a.grad), ("g2", b.grad)):
+            outs[name].copy_(t.detach(), non_blocking=True)
         free[j].record(stream)
 
     def run(nsteps):
@@ -430,18 +528,24 @@ def run_e2e(args, w, dev, stream, spd):
     pts = spd.sum_over_ranks(B * N, dev)
     return {"value": pts / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "d2h": "every output: " + ", ".join(outs),
             "api": "ops.softpool_topk + ops.softpool_gather (autograd) + chamferDist (autograd); pinned host tensors, "
                    "H2D of step i+1 on a copy stream under step i's kernels (two device input sets)"}
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU port of the reference path (cpu_baseline leg and --impl reference)
+# the reference path on the host CPU (cpu_baseline leg and --impl reference)
 # ---------------------------------------------------------------------------------------------
-class CpuPort:
+class CpuRef:
+    """SoftPool: the reference module itself when oracle/_ref/softpool_ref.py was staged (kind "reference": SoftPool.forward
+    of softpool.py:127-171 with `.cuda()` neutralised and the Sorter conv replaced by preset keys, autograd backward),
+    else its op-for-op port (kind "port").  Chamfer: the C restatement of chamfer.cu on all host threads."""
+
     def __init__(self, w, Bs, seed=99):
         import numpy as np
         import torch
         self.np, self.torch = np, torch
+        from oracle import build_ref
         from oracle import chamfer_oracle as co
         from oracle import softpool_torch_port as port
         self.co, self.port = co, port
@@ -455,38 +559,59 @@ class CpuPort:
         self.a = (torch.rand(Bs, N, 3, generator=g) - 0.5).numpy()
         self.b = (torch.rand(Bs, N, 3, generator=g) - 0.5).numpy()
         self.g1 = np.full((Bs, N), 1.0 / (N * Bs), np.float32)
+        self.kind, self.sp = "port", None
+        mod = None if os.environ.get("SPK_BENCH_PORT") == "1" else build_ref.load_ref_softpool(cpu=True)
+        if mod is not None:
+            keys = self.keys
+
+            class PresetKeys(torch.nn.Module):
+                def forward(self, _):
+                    return keys
+            self.sp = mod.SoftPool(regions=R, cabins=cab, sp_ratio=N // k, size_feat=C)
+            self.sp.sorter.conv1d = PresetKeys()
+            self.kind = "reference"
+
+    def describe(self):
+        sp = "reference softpool.py SoftPool.forward + autograd (Sorter conv -> preset keys)" if self.kind == "reference" else \
+            "torch CPU port of softpool.py:134-151 + autograd"
+        return sp + " + C restatement of chamfer.cu, %d threads" % self.threads
 
     def step(self):
-        self.port.forward_backward(self.x, self.keys, self.k, self.cab, self.gc, self.gb)
+        if self.sp is not None:
+            xx = self.x.detach().requires_grad_(True)
+            sp_cube, sp_idx, cabins, id_activa = self.sp(xx)
+            self.torch.autograd.backward([sp_cube, cabins], [self.gc, self.gb])
+        else:
+            self.port.forward_backward(self.x, self.keys, self.k, self.cab, self.gc, self.gb)
         d1, d2, i1, i2 = self.co.forward(self.a, self.b, self.threads)
         _ = d1.mean(1) + d2.mean(1)
         self.co.backward(self.a, self.b, self.g1, self.g1, i1, i2, self.threads)
 
 
 def cpu_baseline(w, budget_s=20.0):
-    probe = CpuPort(w, 2)
+    probe = CpuRef(w, 2)
     probe.step()                                     # first call pays one-time init
     t = time.perf_counter(); probe.step(); t1 = (time.perf_counter() - t) / 2
     Bs = int(max(1, min(w["B"], budget_s / 4.0 / max(t1, 1e-4))))
-    port = CpuPort(w, Bs)
+    port = CpuRef(w, Bs)
     port.step()
     ts = []
     for _ in range(3):
         t = time.perf_counter(); port.step(); ts.append(time.perf_counter() - t)
     best = min(ts)
-    return {"value": Bs * w["N"] / best / 1e6, "unit": UNIT, "cores": port.threads, "kind": "port",
-            "sample": "%d of %d clouds of the same workload, best of 3 steps after 1 warm-up (%.3f s/step); torch CPU port of softpool.py:134-151 + C restatement of chamfer.cu, %d threads" % (Bs, w["B"], best, port.threads)}
+    return {"value": Bs * w["N"] / best / 1e6, "unit": UNIT, "cores": port.threads, "kind": port.kind,
+            "sample": "%d of %d clouds of the same workload, best of 3 steps after 1 warm-up (%.3f s/step); %s" % (Bs, w["B"], best, port.describe())}
 
 
 def run_reference(args, w, rank, world):
     if rank != 0:
         return None
-    probe = CpuPort(w, 2)
+    probe = CpuRef(w, 2)
     probe.step()                                     # first call pays one-time init
     t = time.perf_counter(); probe.step(); t1 = (time.perf_counter() - t) / 2
     budget = 150.0
     Bs = int(max(1, min(w["B"], budget / max(1, args.steps + args.warmup) / max(t1, 1e-4))))
-    port = CpuPort(w, Bs)
+    port = CpuRef(w, Bs)
     for _ in range(args.warmup):
         port.step()
     t0 = time.perf_counter()
@@ -494,11 +619,12 @@ def run_reference(args, w, rank, world):
         port.step()
     ms = (time.perf_counter() - t0) * 1e3 / args.steps
     v = Bs * w["N"] / (ms * 1e-3) / 1e6
-    sample = "%d of %d clouds per step (bounded sample), torch CPU port of the reference SoftPool loop + C restatement of the reference Chamfer kernels" % (Bs, w["B"])
+    sample = "%d of %d clouds per step (bounded sample); %s" % (Bs, w["B"], port.describe())
     return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": w["name"], "per_step_clouds": Bs},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": port.threads, "kind": "port", "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": config_of(w),
+            "measurement": {"per_step_clouds": Bs, "timing": "host wall clock around %d steps" % args.steps},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": port.threads, "kind": port.kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
@@ -510,6 +636,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = WORKLOADS[args.workload]

@@ -122,8 +122,9 @@ size_t chamfer_fwd_workspace_bytes(int B, int n, int m);
  *   float32 expression d = fma(dz,dz, fma(dx,dx, dy*dy)) (its SASS under nvcc's default
  *   -fmad=true), so dist/idx are bit-identical to the reference kernel for finite inputs.
  *   n == 0 or m == 0 leaves zeros in the outputs, like the reference's zero-initialised
- *   buffers (dist_chamfer.py:19-23).  NaN coordinates: unspecified (the reference's result
- *   depends on its 512-point chunking).
+ *   buffers (dist_chamfer.py:19-23).  Samples with a NaN / inf coordinate are evaluated in the
+ *   reference's own loop order (targets in batches of 512, `k==0 || d<best` inside a batch,
+ *   `k2==0 || result>best` across batches), so they match the reference kernel too.
  *   ws / ws_bytes: scratch of at least chamfer_fwd_workspace_bytes(B,n,m), 16-byte aligned. */
 int chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
                     float* dist2, int32_t* idx1, int32_t* idx2, void* ws, size_t ws_bytes,

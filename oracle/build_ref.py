@@ -13,6 +13,10 @@ The reference kernels can only *run* on a GPU, so the resulting module is used b
 ``oracle/chamfer_oracle.c`` (and, through it, our kernels) against the reference
 itself, and by ``bench.py --ref-gpu`` as "the kernel to beat".
 
+``stage_softpool()`` additionally stages the reference's ``softpool.py`` (one file, copied verbatim, NOT into
+git: ``oracle/_ref/`` is git-ignored) as ``oracle/_ref/softpool_ref.py`` so that ``bench.py --impl reference`` and
+its ``ref_gpu`` leg can run the reference module ITSELF on the GPU box, where /root/reference does not exist.
+
 Usage:  python oracle/build_ref.py            (no-op when /root/reference is absent)
 """
 import glob
@@ -45,6 +49,40 @@ def build(verbose=False):
     return built_path()
 
 
+REF_SOFTPOOL = "/root/reference/softpool.py"
+STAGED_SOFTPOOL = os.path.join(OUT, "softpool_ref.py")
+
+
+def stage_softpool():
+    """Copy the reference softpool.py verbatim into oracle/_ref (git-ignored); returns the staged path or None."""
+    if os.path.exists(STAGED_SOFTPOOL):
+        return STAGED_SOFTPOOL
+    if not os.path.exists(REF_SOFTPOOL):
+        return None
+    os.makedirs(OUT, exist_ok=True)
+    import shutil
+    shutil.copyfile(REF_SOFTPOOL, STAGED_SOFTPOOL)
+    return STAGED_SOFTPOOL
+
+
+def load_ref_softpool(cpu):
+    """Import the staged reference softpool.py.  cpu=True neutralises the hard-coded `.cuda()` calls (softpool.py:24,...)
+    to the identity BEFORE the import -- no line of the reference is changed; cpu=False imports it as it is."""
+    p = STAGED_SOFTPOOL if os.path.exists(STAGED_SOFTPOOL) else (REF_SOFTPOOL if os.path.exists(REF_SOFTPOOL) else None)
+    if p is None:
+        return None
+    import importlib.util
+    import torch
+    import torch.nn as nn
+    if cpu:
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        nn.Module.cuda = lambda self, *a, **k: self
+    spec = importlib.util.spec_from_file_location("softpool_ref_cpu" if cpu else "softpool_ref_cuda", p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load_ref():
     """Import the built reference extension (GPU box or here); None if it was never built."""
     p = built_path()
@@ -59,5 +97,6 @@ def load_ref():
 
 
 if __name__ == "__main__":
+    stage_softpool()
     p = build(verbose="-v" in sys.argv)
     print("oracle/_ref:", p if p else "unavailable (no /root/reference)")

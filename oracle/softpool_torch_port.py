@@ -18,15 +18,15 @@ def forward(x, keys, k, cab=8):
     B, C, N = x.shape
     R = keys.shape[1]
     id_activa = torch.argmax(keys, dim=1)
-    sp_cube = torch.zeros(B, C, R, k)
-    sp_idx = torch.zeros(B, R + 3, R, k)
+    sp_cube = torch.zeros(B, C, R, k, device=x.device)
+    sp_idx = torch.zeros(B, R + 3, R, k, device=x.device)
     for region in range(R):
         _, order = torch.sort(keys[:, region, :], dim=1, descending=True)
         top = order[:, :k]
         sp_cube[:, :, region, :] = torch.gather(x, dim=2, index=top.unsqueeze(1).repeat(1, C, 1))
         sp_idx[:, :, region, :] = top.unsqueeze(1).repeat(1, R + 3, 1)
     per = k // cab
-    cabins = torch.zeros(B, C, R, cab)
+    cabins = torch.zeros(B, C, R, cab, device=x.device)
     for w in range(cab):
         cabins[:, :, :, w] = torch.max(sp_cube[:, :, :, w * per:(w + 1) * per], dim=3, keepdim=False)[0]
     return sp_cube, sp_idx, cabins, id_activa

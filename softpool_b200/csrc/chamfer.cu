@@ -43,10 +43,13 @@ chamfer_nn_exact_kernel(const float* __restrict__ xyz1, const float* __restrict_
     for (int u = 0; u < CH_QPT; ++u) {
         const int q = min(q0 + threadIdx.x + u * CH_THREADS, nq - 1);
         qx[u] = __ldg(Q + 3 * q + 0); qy[u] = __ldg(Q + 3 * q + 1); qz[u] = __ldg(Q + 3 * q + 2);
-        // reference: `k==0 || d<best` -- the first target initialises the running best
-        best[u] = ref_sqdist(qx[u], qy[u], qz[u], __ldg(T + 0), __ldg(T + 1), __ldg(T + 2));
-        besti[u] = 0;
+        best[u] = 0.f; besti[u] = 0;
     }
+    // The reference's loop order, statement for statement (chamfer.cu:16-129): targets in batches of 512, a batch's first
+    // target initialises the batch minimum (`k==0 || d<best`), the stored result is replaced only when strictly greater
+    // (`k2==0 || result>best`).  For finite inputs that is the first minimum; for NaN distances it is what the reference does.
+    constexpr int REF_BATCH = 512;
+    static_assert(CH_CHUNK % REF_BATCH == 0, "a shared-memory chunk holds whole reference batches");
     for (int k0 = 0; k0 < nt; k0 += CH_CHUNK) {
         const int cnt = min(CH_CHUNK, nt - k0);
         __syncthreads();
@@ -55,14 +58,26 @@ chamfer_nn_exact_kernel(const float* __restrict__ xyz1, const float* __restrict_
             tgt[i] = make_float4(__ldg(s), __ldg(s + 1), __ldg(s + 2), 0.f);
         }
         __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < cnt; ++k) {
-            const float4 t = tgt[k];
+        for (int kb = 0; kb < cnt; kb += REF_BATCH) {
+            const int end = min(cnt, kb + REF_BATCH);
+            float bb[CH_QPT]; int bi[CH_QPT];
+            {
+                const float4 t = tgt[kb];
 #pragma unroll
-            for (int u = 0; u < CH_QPT; ++u) {
-                const float d = ref_sqdist(qx[u], qy[u], qz[u], t.x, t.y, t.z);
-                if (d < best[u]) { best[u] = d; besti[u] = k0 + k; }
+                for (int u = 0; u < CH_QPT; ++u) { bb[u] = ref_sqdist(qx[u], qy[u], qz[u], t.x, t.y, t.z); bi[u] = k0 + kb; }
             }
+#pragma unroll 4
+            for (int k = kb + 1; k < end; ++k) {
+                const float4 t = tgt[k];
+#pragma unroll
+                for (int u = 0; u < CH_QPT; ++u) {
+                    const float d = ref_sqdist(qx[u], qy[u], qz[u], t.x, t.y, t.z);
+                    if (d < bb[u]) { bb[u] = d; bi[u] = k0 + k; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < CH_QPT; ++u)
+                if (k0 + kb == 0 || best[u] > bb[u]) { best[u] = bb[u]; besti[u] = bi[u]; }
         }
     }
 #pragma unroll

@@ -355,6 +355,23 @@ __device__ __forceinline__ float ref_sqdist_tc(float x1, float y1, float z1, flo
     const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
+// NmDistanceKernel statement for statement (reference chamfer.cu:16-129): targets in batches of 512, the batch's first
+// target initialises the running best (`k==0 || d<best`), the stored result is replaced only when strictly greater
+// (`k2==0 || result>best`).  Used for samples with non-finite coordinates / hopeless conditioning, where the result
+// depends on exactly this order (a NaN distance at a batch start hides the rest of that batch).
+__device__ __forceinline__ void ref_order_nn(const float* __restrict__ T, int nt, float qx, float qy, float qz, float& res, int& res_i) {
+    res = 0.f; res_i = 0;
+    for (int k2 = 0; k2 < nt; k2 += 512) {
+        const int end_k = min(nt, k2 + 512) - k2;
+        float best = 0.f; int best_i = 0;
+        for (int k = 0; k < end_k; ++k) {
+            const float* t = T + 3 * (size_t)(k2 + k);
+            const float d = ref_sqdist_tc(qx, qy, qz, __ldg(t), __ldg(t + 1), __ldg(t + 2));
+            if (k == 0 || d < best) { best = d; best_i = k + k2; }
+        }
+        if (k2 == 0 || res > best) { res = best; res_i = best_i; }
+    }
+}
 __device__ __forceinline__ void exact_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four exact warps
 
 // ---------------------------------------------------------------------------------------------
@@ -584,6 +601,10 @@ chamfer_tc_kernel(const TcParams p) {
             const float t0x = __ldg(Tx + 3 * (size_t)t_first), t0y = __ldg(Tx + 3 * (size_t)t_first + 1), t0z = __ldg(Tx + 3 * (size_t)t_first + 2);
             float best_d = 0.f;
             int best_i = t_first;
+            // non-finite / hopelessly conditioned sample: the reference's own loop order decides (first sub-job only; the
+            // super-block loop below then only keeps the pipeline's barriers moving)
+            const bool ref_here = eval_all && sb0 == 0;
+            if (ref_here && live) ref_order_nn(Tx, nt, qx, qy, qz, best_d, best_i);
 
             for (int sb = 0; sb < n_sb; ++sb) {
                 const uint32_t sbi = sb_it + sb, pb = sbi & 1;
@@ -604,7 +625,7 @@ chamfer_tc_kernel(const TcParams p) {
                 for (int i = 3; i + 1 < NW; i += 2) rm = __vimin3_u16x2(rm, cm[i], cm[i + 1]);
                 rm = __vminu2(rm, cm[NW - 1]);
                 const uint32_t r16 = min(rm & 0xFFFFu, rm >> 16);
-                if (sb == 0) best_d = ref_sqdist_tc(qx, qy, qz, t0x, t0y, t0z);
+                if (sb == 0 && !eval_all) best_d = ref_sqdist_tc(qx, qy, qz, t0x, t0y, t0z);
                 // threshold: min(row minimum, exact best) widened by the fp16 rounding of the accumulator
                 // (relative, 2^-8 = 4 ulp) and the error bound of the operands (absolute, tau), rounded UP to fp16
                 float thr = fminf(__half2float(__ushort_as_half((unsigned short)r16)), fmaf(best_d, scale2, bias));
@@ -614,7 +635,7 @@ chamfer_tc_kernel(const TcParams p) {
                 // mask bit i (i < 16): chunk in the low lane of word i, bit 16+i: its high lane; words 16..31 in the upper half
                 uint32_t m_lo = 0, m_hi = 0;
                 if (eval_all) {
-                    m_lo = m_hi = 0xFFFFFFFFu;
+                    m_lo = m_hi = 0u;                                 // (result already formed by ref_order_nn)
                 } else {
                     // per lane (0x8000 | t) - c keeps bit 15 exactly when c <= t (both are 15-bit values: no borrow
                     // crosses the lanes); the bits 15 / 31 of word i go to mask bits i / 16+i
@@ -668,9 +689,11 @@ chamfer_tc_kernel(const TcParams p) {
             if (NS == 1 && p.loss != nullptr)
                 loss_contribute(p, b, dir, lane, live ? best_d : 0.f);
             if (live) {
-                if (NS == 1) {
-                    ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = best_d;
-                    ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = best_i;
+                if (NS == 1 || eval_all) {
+                    if (NS == 1 || ref_here) {                     // (split + non-finite: the first sub-job holds the whole answer)
+                        ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = best_d;
+                        ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = best_i;
+                    }
                 } else {
                     // distances are >= +0: their bit patterns order like the values, the index breaks ties
                     // downwards -> the 64-bit minimum over the sub-jobs IS the first minimum
@@ -692,14 +715,16 @@ chamfer_tc_kernel(const TcParams p) {
                 }
                 exact_bar();
                 float merged = 0.f;
-                if (S.last && live) {
+                if (eval_all) {
+                    if (ref_here && p.loss != nullptr) loss_contribute(p, b, dir, lane, live ? best_d : 0.f);
+                } else if (S.last && live) {
                     unsigned long long v;
                     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"((dir ? p.packed2 : p.packed1) + (size_t)b * nq + gq) : "memory");
                     merged = __uint_as_float((unsigned)(v >> 32));
                     ((dir ? p.dist2 : p.dist1) + (size_t)b * nq)[gq] = merged;
                     ((dir ? p.idx2 : p.idx1) + (size_t)b * nq)[gq] = (int)(unsigned)v;
                 }
-                if (S.last && p.loss != nullptr)                   // exactly one sub-job per query tile gets here
+                if (!eval_all && S.last && p.loss != nullptr)      // exactly one sub-job per query tile gets here
                     loss_contribute(p, b, dir, lane, merged);
                 exact_bar();                                       // S.last is rewritten by the next split job
             }

@@ -53,6 +53,16 @@ def sum_over_ranks(value, device="cpu"):
     return _reduce(value, dist.ReduceOp.SUM, device)
 
 
+def gather_over_ranks(value, device="cpu"):
+    """[value of rank 0, ..., value of rank world-1] on every rank (reporting only)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [float(value)]
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
+
+
 def barrier():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()

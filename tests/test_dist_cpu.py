@@ -24,6 +24,7 @@ def _worker(rank, world, port, q):
     spd.barrier()
     t = spd.max_over_ranks(1.0 + r)            # slowest rank defines the step time
     units = spd.sum_over_ranks(hi - lo)        # whole-job units = sum of the shards
+    assert spd.gather_over_ranks(10.0 + r) == [10.0, 11.0]      # per-rank step times, reported as min / median / max
     q.put((r, lo, hi, t, units))
     torch.distributed.destroy_process_group()
 
