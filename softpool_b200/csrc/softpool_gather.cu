@@ -81,7 +81,6 @@ sp_gather_fwd_kernel(const GatherFwdParams p) {
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
     pdl_trigger();
     __syncthreads();
-    pdl_wait();
 
     long long g_lo, g_hi;
     cta_range(p.rows, g_lo, g_hi);
@@ -99,6 +98,9 @@ sp_gather_fwd_kernel(const GatherFwdParams p) {
     } else {
         for (int i = 0; i < 2 && g_pref < g_hi; ++i) g_pref += tile_rows(g_pref, g_hi, T, C);
     }
+    // The first two x tiles are in flight; only now wait for the kernel before this one (the top-k, which produces idx
+    // and lets its dependents start early -- after ITS wait, so x was complete before either kernel began).
+    pdl_wait();
 
     const int wl = p.cab > 0 ? p.k / p.cab : 0;          // window length
     const int G = p.cab_fast ? (wl >> 2) : 1;            // work items (lanes) per window

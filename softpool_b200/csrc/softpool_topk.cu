@@ -77,6 +77,9 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     const float* krow = keys + (size_t)row * N;
     pdl_trigger();
     pdl_wait();
+#ifndef SPK_NO_TOPK_TRIGGER
+    pdl_launch_dependents();     // see spk_common.cuh: the gather's first x tiles load under this kernel
+#endif
 #ifdef SPK_TIMING
     long long tq[8]; tq[0] = clock64();
 #define TQ(i) tq[i] = clock64()

@@ -149,6 +149,10 @@ __device__ __forceinline__ void pdl_trigger() {
 #endif
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Unconditional trigger, used by sp_topk_kernel only and only AFTER its own pdl_wait(): everything that preceded the
+// top-k in the stream is then complete, so the next kernel (the gather) may safely read ITS OTHER inputs (x) in its
+// prologue, before its own pdl_wait() -- the x tiles stream in while the latency-bound top-k still runs.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // Tail trigger (compile with -DSPK_PDL_TAIL; OFF by default): called by every thread once its main loop is
 // done; the next kernel's CTAs then launch while this kernel drains (their pdl_wait() still waits for this
 // kernel's completion and memory flush, so placement is a performance matter only).  Measured: -0.7 us per
