@@ -822,7 +822,9 @@ int chamfer_dense_forward(const float* xyz1, const float* xyz2, int B, int n, in
     SPK_CUDA(cudaFuncSetAttribute(chamfer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long jobs = ((long long)tp.tiles1 * S1 + (long long)tp.tiles2 * S2) * B;
     int grid = (int)std::min<long long>(jobs, 2LL * sm_count());         // persistent: 2 CTAs per SM
+#ifdef SPK_EXPERIMENT
     if (const char* e = getenv("SPK_TC_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
+#endif
     SPK_CUDA(launch_k(chamfer_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tp));
     return SPK_OK;
 }

@@ -414,6 +414,9 @@ sp_gather_bwd_push_kernel(const GatherBwdPushParams p) {
                 bulk_commit();
             }
         } else {
+            // the window-max fold wrote the staged gradient tile with generic stores and the next bulk copy refills that
+            // slot through the async proxy: order the two (the bulk_out branch above fences already)
+            if (p.bulk_in && p.g_cabins != nullptr) fence_proxy_async_smem();
             for (int i = tid; i < rows * N; i += nthr) dst[i] = ac[i];
             __syncthreads();
         }
@@ -674,9 +677,33 @@ sp_gather_bwd_pull_kernel(const GatherBwdPullParams p) {
 
 }  // namespace spk
 
+// Tuning / timing knobs (SPK_FWD_*, SPK_PULL_*, SPK_BWD_SMEM_KB, SPK_BWD_RING): read ONLY in builds made with
+// SPK_NVCC_EXTRA=-DSPK_EXPERIMENT -- a stray environment variable cannot change how the shipped library runs, and
+// SPK_PULL_DBG (which skips work and so returns WRONG results, for timing only) does not exist in it at all.
+static const char* tune_env(const char* name) {
+#ifdef SPK_EXPERIMENT
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
+
+// resident CTAs of a persistent kernel; the occupancy query is cached per (kernel, width, shared memory, device)
 static int occupancy_slots(const void* kernel, int threads, size_t smem, int cap_per_sm) {
+    struct Entry { const void* k; int threads; size_t smem; int dev; int per_sm; };
+    static thread_local Entry cache[16];
+    static thread_local int n_cache = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].k == kernel && cache[i].threads == threads && cache[i].smem == smem && cache[i].dev == dev) per_sm = cache[i].per_sm;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        cache[n_cache % 16] = Entry{kernel, threads, smem, dev, per_sm};
+        ++n_cache; if (n_cache > 16) n_cache = 16;
+    }
     if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;
     return per_sm * spk::sm_count();
 }
@@ -725,15 +752,15 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
     // tile size / CTA width: 256 threads with two ~32 KB tiles (3 CTAs per SM), or -- SPK_FWD_THREADS=128 --
     // narrow CTAs with two ~16 KB tiles (6 CTAs per SM)
     int threads = 256;
-    if (const char* e = getenv("SPK_FWD_THREADS")) threads = atoi(e) <= 128 ? 128 : 256;
+    if (const char* e = tune_env("SPK_FWD_THREADS")) threads = atoi(e) <= 128 ? 128 : 256;
     size_t tile_target = threads == 128 ? 16 * 1024 : 32 * 1024;
-    if (const char* e = getenv("SPK_FWD_TILE_KB")) tile_target = (size_t)atoi(e) * 1024;
+    if (const char* e = tune_env("SPK_FWD_TILE_KB")) tile_target = (size_t)atoi(e) * 1024;
     int T = (int)std::max<size_t>(1, std::min<size_t>(16, tile_target / row_bytes));
     while (T > 1 && fixed + 2 * (size_t)T * row_bytes > budget) --T;
     T = std::min(T, C);
     p.T = T;
     // the per-group hoisting only pays when a tile holds several rows (measured: N=2048 33 vs 34.5 us; one row per tile, N=8192: 169 vs 145 us)
-    p.q_cols = T >= 2 && p.vec4 && ((RK >> 2) % threads) == 0 && (!want_cab || p.cab_fast) && !getenv("SPK_FWD_NO_QCOLS");
+    p.q_cols = T >= 2 && p.vec4 && ((RK >> 2) % threads) == 0 && (!want_cab || p.cab_fast) && !tune_env("SPK_FWD_NO_QCOLS");
     const size_t smem = fixed + 2 * (size_t)T * row_bytes;
     auto launch = [&](auto kern, int nt) -> int {
         if (smem > 48 * 1024)
@@ -777,7 +804,7 @@ static int gather_bwd_push(const float* g_cube, const float* g_cabins, const int
         return fail(SPK_E_UNSUPPORTED, "sp_gather_bwd_f32: N=%d, R*k=%lld do not fit shared memory", N, RK);
     p.ng = 2;
     size_t target = 72 * 1024;
-    if (const char* e = getenv("SPK_BWD_SMEM_KB")) target = (size_t)atoi(e) * 1024;      // tuning knob
+    if (const char* e = tune_env("SPK_BWD_SMEM_KB")) target = (size_t)atoi(e) * 1024;      // tuning knob
     int T = (int)std::max<size_t>(1, std::min<size_t>(8, (target - std::min<size_t>(fixed, target)) / per_T));
     T = std::min(T, C);
     p.T = T;
@@ -787,7 +814,7 @@ static int gather_bwd_push(const float* g_cube, const float* g_cabins, const int
         // measured on B200: a deeper ring (3-4 tiles in flight) is SLOWER at config A (28.0 vs 23.5 us), so the
         // default stays at 2; SPK_BWD_RING=3|4 re-enables it for experiments
         int want = 2;
-        if (const char* e = getenv("SPK_BWD_RING")) want = std::max(2, std::min(4, atoi(e)));
+        if (const char* e = tune_env("SPK_BWD_RING")) want = std::max(2, std::min(4, atoi(e)));
         while (p.ng < want && smem + gtile <= std::max(target, (size_t)74 * 1024)) { smem += gtile; ++p.ng; }
     }
     if (smem > 48 * 1024)
@@ -826,15 +853,15 @@ static int gather_bwd_pull(const float* g_cube, const float* g_cabins, const int
     const size_t budget = (size_t)max_optin_smem();
     const size_t fixed = 128 + (((((size_t)N + 3) & ~(size_t)3) * 2 + 127) & ~(size_t)127) + (((size_t)RK * 2 + 127) & ~(size_t)127);
     size_t target = 75 * 1024;                                     // three CTAs per SM
-    if (const char* e = getenv("SPK_PULL_SMEM_KB")) target = (size_t)atoi(e) * 1024;
+    if (const char* e = tune_env("SPK_PULL_SMEM_KB")) target = (size_t)atoi(e) * 1024;
     const int wins = R * p.cab;
     // the window-max gradient rides along as bulk copies when every group's byte ranges are 16-byte multiples
     p.cab_bulk = g_cabins != nullptr && (wins % 8) == 0 && (((uintptr_t)g_cabins & 15) == 0) && (((uintptr_t)cab_arg & 15) == 0);
-    if (getenv("SPK_PULL_NOCABBULK")) p.cab_bulk = 0;
+    if (tune_env("SPK_PULL_NOCABBULK")) p.cab_bulk = 0;
     // T rows per group: as many as keep three CTAs per SM; tables / tiles too large for that: up to two
     // rows in one wide CTA per SM
     int T = 8;
-    if (const char* e = getenv("SPK_PULL_T")) T = atoi(e);
+    if (const char* e = tune_env("SPK_PULL_T")) { T = atoi(e); if (T != 1 && T != 2 && T != 4 && T != 8) return fail(SPK_E_BADARG, "SPK_PULL_T must be 1, 2, 4 or 8"); }
     else {
         while (T > 1 && fixed + 2 * pull_slot_bytes(T, (int)RK, wins, p.cab_bulk) > target) T >>= 1;
         if (T == 1 && fixed + 2 * pull_slot_bytes(1, (int)RK, wins, p.cab_bulk) > target &&
@@ -845,19 +872,21 @@ static int gather_bwd_pull(const float* g_cube, const float* g_cabins, const int
     const size_t tile = pull_slot_bytes(T, (int)RK, wins, p.cab_bulk);
     if (fixed + 2 * tile > budget) return 1;
     int ng = 2;
-    if (const char* e = getenv("SPK_PULL_NG")) ng = atoi(e);
+    if (const char* e = tune_env("SPK_PULL_NG")) ng = atoi(e);
     ng = std::max(2, std::min(8, ng));
     while (ng > 2 && fixed + (size_t)ng * tile > std::max(target, fixed + 2 * tile)) --ng;
     p.ng = ng;
     p.dbg = 0;
-    if (const char* e = getenv("SPK_PULL_DBG")) p.dbg = atoi(e);
+#ifdef SPK_EXPERIMENT
+    if (const char* e = getenv("SPK_PULL_DBG")) p.dbg = atoi(e);      // timing only: skips work, results WRONG
+#endif
     const size_t smem = fixed + (size_t)ng * tile;
     // CTA width: narrow CTAs (128 threads) put more independent CTAs on an SM, so one CTA's table build /
     // tile wait / fold overlaps another's stores (measured at config A: 14.0 us vs 18.6 us with 256);
     // with at most two resident CTAs (large tables / tiles) 512 threads keep enough warps per SM
     int threads = 128;
     if (T < 8 && (228 * 1024) / (smem + 1024) <= 2) threads = 512;
-    if (const char* e = getenv("SPK_PULL_THREADS")) threads = atoi(e);
+    if (const char* e = tune_env("SPK_PULL_THREADS")) threads = atoi(e);
     if (T == 8 && threads > 256) threads = 256;
 #define SPK_PULL_CASE(TT)                                                            \
     case TT:                                                                         \

@@ -60,7 +60,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot /*[8]*/
 }
 
 __global__ void __launch_bounds__(TOPK_THREADS)
-sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K2,
+sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K2, int vec_ok,
                int32_t* __restrict__ idx, float* __restrict__ sp_idx,
                int64_t* __restrict__ id_activa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -102,7 +102,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     // ---- 1. load: thread t owns the E consecutive points n = t*E .. t*E+E-1 ------------------------
     // (all loads are issued before the first use: order_key is branch-free, nothing serialises them)
     const int n0 = tid * E;
-    if ((E & 3) == 0 && (N & 3) == 0) {
+    if (vec_ok && (E & 3) == 0 && (N & 3) == 0) {
         for (int e0 = 0; e0 < E; e0 += 16) {
             float4 v[4];
 #pragma unroll
@@ -338,14 +338,14 @@ extern "C" int sp_topk_f32(const float* keys, int B, int R, int N, int k, int32_
     if (!keys || !idx) return fail(SPK_E_BADARG, "sp_topk_f32: null keys/idx");
     if (N > 16384) return fail(SPK_E_UNSUPPORTED, "sp_topk_f32: N=%d > 16384 (row must fit shared memory)", N);
     if (sp_idx && N >= (1 << 24)) return fail(SPK_E_UNSUPPORTED, "sp_topk_f32: N >= 2^24 not exact in float32");
-    if ((N & 3) == 0 && ((uintptr_t)keys & 15)) return fail(SPK_E_ALIGN, "sp_topk_f32: keys must be 16-byte aligned");
+    const int vec_ok = ((uintptr_t)keys & 15) == 0;     // misaligned keys: scalar loads (the gather and Chamfer kernels do the same)
     const int K2 = max(2, next_pow2(k));
     int E = (N + TOPK_THREADS - 1) / TOPK_THREADS;
     if (E > 4) E = (E + 3) & ~3;                       // float4 path wants E % 4 == 0
     const size_t smem = (size_t)K2 * sizeof(uint64_t) + (size_t)E * TOPK_THREADS * sizeof(uint32_t) + 3 * 8 * 16 * sizeof(int);
     if (smem > 48 * 1024)
         SPK_CUDA(cudaFuncSetAttribute(sp_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SPK_CUDA(launch_k(sp_topk_kernel, dim3(B * R), dim3(TOPK_THREADS), smem, (cudaStream_t)stream, keys, R, N, k, E, K2, idx, sp_idx, id_activa));
+    SPK_CUDA(launch_k(sp_topk_kernel, dim3(B * R), dim3(TOPK_THREADS), smem, (cudaStream_t)stream, keys, R, N, k, E, K2, vec_ok, idx, sp_idx, id_activa));
     return SPK_OK;
 }
 

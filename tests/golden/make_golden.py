@@ -117,8 +117,30 @@ def special_x(x):
     return x
 
 
+def run_feat(ref, name, B, N, R, sp_ratio, seed):
+    """Reference SoftPoolFeat (softpool.py:174-241): PointNet MLP + BatchNorm (train mode, as the reference trains) + SoftPool
+    + the index bookkeeping; stores the live weights (conv1-3, bn1-3, sorter.conv1d), the input, the MLP output, the keys and
+    the three returned tensors."""
+    torch.sort = _orig_sort
+    torch.manual_seed(seed)
+    m = ref.SoftPoolFeat(num_points=N, regions=R, sp_points=N, sp_ratio=sp_ratio)
+    x = torch.rand(B, 3, N) - 0.5
+    with torch.no_grad():
+        feat = m.mlp(x)
+        keys = m.softpool.sorter.conv1d(feat)
+        sp_cube, cabins, sp_idx = m(x)
+    sd = {k: v.numpy() for k, v in m.state_dict().items() if not k.startswith("softpool.conv2d_") and "num_batches" not in k
+          and "running_" not in k}
+    np.savez_compressed(os.path.join(OUT, "softpool_%s.npz" % name), meta=np.array([B, N, R, sp_ratio], dtype=np.int64),
+                        x=x.numpy(), feat=feat.numpy(), keys=keys.numpy(), sp_cube=sp_cube.numpy(), cabins=cabins.numpy(),
+                        sp_idx=sp_idx.numpy(), **{"w_" + k: v for k, v in sd.items()})
+    print("%-10s SoftPoolFeat B=%d N=%d R=%d sp_ratio=%d -> sp_cube %s cabins %s sp_idx %s" %
+          (name, B, N, R, sp_ratio, tuple(sp_cube.shape), tuple(cabins.shape), tuple(sp_idx.shape)))
+
+
 def main():
     ref = load_reference()
+    run_feat(ref, "feat", 2, 128, 8, 8, seed=6)
     # BASELINE.json config 1: (B=4, N=512, C=32), R=8, sp_ratio=8 -> k=64
     run_case(ref, "c1", 4, 32, 512, 8, 8, 8, seed=0)
     # ties, NaN, +-inf, +-0 in the keys and in the features

@@ -238,6 +238,86 @@ def test_full_size_properties():
         torch.testing.assert_close(gx, xr.grad, rtol=RTOL_GRAD, atol=1e-5)
 
 
+@pytest.mark.parametrize("k", [32, 256])
+def test_full_size_vs_oracle(k):
+    """BASELINE config 2 at its full size (B=32, C=256, N=2048, R=8; k=32 and the reference operating point k=256),
+    forward and backward, against the numpy oracle: indices, copies and window maxima bit-exact, grad_x bit-identical
+    to the oracle's ascending-region summation order."""
+    rng = np.random.default_rng(2048 + k)
+    B, C, N, R, cab = 32, 256, 2048, 8, 8
+    x = rng.standard_normal((B, C, N), dtype=np.float32)
+    keys = rng.standard_normal((B, R, N), dtype=np.float32)
+    g_cube = rng.standard_normal((B, C, R, k), dtype=np.float32)
+    g_cab = rng.standard_normal((B, C, R, cab), dtype=np.float32)
+    out = run_cuda(x, keys, k, cab, g_cube, g_cab)
+    ref = so.softpool_forward(x, keys, k, cab)
+    assert np.array_equal(out["idx"], ref["idx"])
+    assert np.array_equal(out["sp_idx"], ref["sp_idx"]) and np.array_equal(out["id_activa"], ref["id_activa"])
+    assert np.array_equal(bits(out["sp_cube"]), bits(ref["sp_cube"])) and np.array_equal(bits(out["cabins"]), bits(ref["cabins"]))
+    ref_g = so.softpool_backward(g_cube, g_cab, ref["idx"], ref["cab_arg"], N)
+    assert np.array_equal(bits(out["grad_x"]), bits(ref_g))
+
+
+def test_tie_order_is_cuda_torch_sort():
+    """The reference's deployment path is torch.sort on CUDA tensors (softpool.py:140, default stable=False).  On tie-heavy
+    keys (quantised to 1/16, all-equal rows, +-0) the library's order -- ties keep ascending point index -- must be what
+    CUDA torch.sort delivers, both with stable=True and with the reference's default call."""
+    from softpool_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for (B, R, N, k) in [(4, 8, 2048, 256), (2, 8, 2048, 32), (3, 5, 1000, 125), (1, 2, 16384, 2048)]:
+        keys = torch.round(torch.randn(B, R, N, generator=g) * 16) / 16
+        keys[0, 0, :] = 0.75                                   # an all-equal row
+        keys[0, 1, ::2] = 0.0; keys[0, 1, 1::2] = -0.0          # +0 / -0 tie
+        kt = keys.to(dev())
+        idx, _, _ = ops.softpool_topk(kt, k)
+        for stable in (True, False):
+            ref = torch.stack([torch.sort(kt[:, r, :], dim=1, descending=True, stable=stable)[1][:, :k] for r in range(R)], 1)
+            assert torch.equal(idx.long(), ref), "B=%d R=%d N=%d k=%d stable=%s" % (B, R, N, k, stable)
+
+
+def test_softpoolfeat_matches_reference_golden():
+    """Reference SoftPoolFeat (softpool.py:174-241, train-mode BatchNorm) on tests/golden/softpool_feat.npz: the fixture's
+    live weights are loaded into the drop-in module.  cuDNN/cuBLAS convolutions on the GPU round differently from the CPU
+    run that made the fixture, so keys are compared within 1e-4 and the index lists row by row: a (sample, region) row
+    whose golden key gaps are all above that rounding must be IDENTICAL, and on identical rows the gathered features and
+    window maxima must match within 1e-4."""
+    import softpool_b200 as spb
+    g = np.load(os.path.join(GOLDEN, "softpool_feat.npz"))
+    B, N, R, sp_ratio = [int(v) for v in g["meta"]]
+    k = N // sp_ratio
+    torch.manual_seed(0)
+    m = spb.SoftPoolFeat(num_points=N, regions=R, sp_points=N, sp_ratio=sp_ratio).to(dev())
+    sd = {name[2:]: torch.from_numpy(g[name]) for name in g.files if name.startswith("w_")}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(key.startswith("softpool.conv2d_") or "running_" in key or "num_batches" in key for key in missing)
+    m.train()
+    x = torch.from_numpy(g["x"]).to(dev())
+    with torch.no_grad():
+        feat = m.mlp(x)
+        keys = m.softpool.sorter.conv1d(feat)
+        sp_cube, cabins, sp_idx = m(x)
+    np.testing.assert_allclose(feat.cpu().numpy(), g["feat"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(keys.cpu().numpy(), g["keys"], rtol=1e-4, atol=1e-5)
+    assert sp_cube.shape == g["sp_cube"].shape and cabins.shape == g["cabins"].shape and sp_idx.shape == g["sp_idx"].shape
+    ours = sp_idx.cpu().numpy().reshape(B, R + 3, R, k)
+    gold = g["sp_idx"].reshape(B, R + 3, R, k)
+    assert (ours == ours[:, :1]).all()                          # the index list is replicated R + 3 times
+    gk = g["keys"]
+    cube_o = sp_cube.cpu().numpy().reshape(B, 256, R, k); cube_g = g["sp_cube"].reshape(B, 256, R, k)
+    same_rows = 0
+    for b in range(B):
+        for r in range(R):
+            srt = np.sort(gk[b, r])[::-1]
+            safe = np.abs(np.diff(srt[:k + 1])).min() > 1e-4    # every gap around the selected prefix is above the rounding noise
+            same = np.array_equal(ours[b, 0, r], gold[b, 0, r])
+            assert same or not safe, "row (%d, %d) differs although its key gaps are wide" % (b, r)
+            if same:
+                same_rows += 1
+                np.testing.assert_allclose(cube_o[b, :, r], cube_g[b, :, r], rtol=1e-4, atol=1e-5)
+                np.testing.assert_allclose(cabins.cpu().numpy()[b, :, r], g["cabins"][b, :, r], rtol=1e-4, atol=1e-5)
+    assert same_rows >= (B * R) // 2                            # the comparison really happened
+
+
 def test_errors_are_loud():
     from softpool_b200 import ops
     with pytest.raises(RuntimeError):
@@ -303,6 +383,7 @@ PULL_SHAPES = [
     (2, 7, 16384, 8, 2048, 8),         # large tables: one wide CTA per SM
     (1, 3, 8192, 8, 8192, 8),          # R*k >= 65535: slots do not fit u16 -> the push kernel serves it
     (2, 300, 512, 64, 8, 8),           # many regions, C not a multiple of the group
+    (3, 9, 1001, 4, 64, 8),            # push: R*k % 4 == 0 (bulk gradient tiles) but N % 4 != 0 (plain stores): the proxy fence after the window-max fold
 ]
 
 
