@@ -124,7 +124,6 @@ struct SortParams {
     const float* xyz[2];                 // (B, n[c], 3)
     int n[2], n_pad[2], nc[2], nc_pad[2];
     float4* S[2];                        // sorted points (x, y, z, original index bits), nc_pad * 16 per sample
-    unsigned char* A[2];                 // query operand rows, n_pad * 32 bytes per sample
     unsigned char* Bc[2];                // chunk-centre operand rows, nc_pad * 32 bytes per sample
     float4* box[2];                      // per chunk {lo.xyz, capped flag}, {hi.xyz, 0}; nc_pad * 2 per sample
     uint16_t* cellstart[2];              // first sorted position of every Morton cell, SORT_CELLS per sample
@@ -332,7 +331,6 @@ chamfer_sort_kernel(const SortParams p) {
     SORT_PHASE();                 // 4: cell starts + permutation
     // ---- sorted outputs: points, query operand rows, per-chunk box / centre / radius ------------------------------------
     float4* S = p.S[cl] + (size_t)b * nc_pad * TC_CHUNK;
-    unsigned char* A = p.A[cl] + (size_t)b * n_pad * 32;
     unsigned char* Bc = p.Bc[cl] + (size_t)b * nc_pad * 32;
     float4* box = p.box[cl] + (size_t)b * nc_pad * 2;
     float4* cst = reinterpret_cast<float4*>(cellrank);          // per chunk (centre, 1.5 r^2 scaled); cellrank is dead: n * 4 >= nc * 16 bytes
@@ -348,7 +346,6 @@ chamfer_sort_kernel(const SortParams p) {
             x = X[3 * orig]; y = X[3 * orig + 1]; z = X[3 * orig + 2];
         }
         S[s] = make_float4(x, y, z, __int_as_float(orig));
-        write_a_row(A, s, real, (x - cx) * sc, (y - cy) * sc, (z - cz) * sc);
         // chunk = 16 consecutive lanes
         float l[3] = {x, y, z}, h[3] = {real ? x : -INFINITY, real ? y : -INFINITY, real ? z : -INFINITY};   // (!real: x = y = z = +inf)
 #pragma unroll
@@ -490,7 +487,7 @@ __device__ __forceinline__ void ref_order_nn(const float* __restrict__ T, int nt
 struct SearchParams {
     const float* xyz[2];
     int n[2], n_pad[2], nc[2], nc_pad[2];
-    const float4* S[2]; const unsigned char* A[2]; const unsigned char* Bc[2]; const float4* box[2];
+    const float4* S[2]; const unsigned char* Bc[2]; const float4* box[2];
     const uint16_t* cellstart[2]; const ChamferGrid* grid[2];
     const ChamferMeta* meta;
     float* dist[2]; int32_t* idx[2];
@@ -508,19 +505,24 @@ __device__ unsigned long long g_tc_dbg[8];      // 0 queries x passes, 1 step-1 
 constexpr int TC_PASS_TARGETS = TC_NC * TC_CHUNK;          // 2048 sorted targets per pass
 constexpr int TC_QCAP = 1536;                              // candidate queue slots per pass (overflow: the owner evaluates at once)
 
+// Shared memory of the search kernel.  The tail region holds, for a one-pass target cloud (<= 2048 points, STAGED), the
+// cloud's chunk boxes and its sorted points -- every box test and exact distance then reads shared memory; for larger
+// clouds only the chunk boxes of the current and the next pass (double-buffered): ~1 chunk per query and pass is
+// evaluated there, straight from global memory / L2.
 struct __align__(128) SearchSmem {
-    unsigned char a_tile[TC_TILE_BYTES];         // query operand tile of the job whose MMAs are being issued
+    unsigned char a_tile[TC_TILE_BYTES];         // query operand tile of the job whose MMAs are being issued (written by the CTA itself)
     unsigned char b_tile[2][TC_TILE_BYTES];      // chunk-centre operand tile, per step parity
-    float4 box[TC_NC * 2];                       // this pass's chunk boxes {lo, flag}, {hi, 0}
-    float4 tgt[TC_PASS_TARGETS];                 // this pass's sorted targets (x, y, z, original index)
-    float4 q4[TC_TILE];                          // this job's queries (x, y, z, original index)
+    float4 q4[TC_TILE];                          // this job's queries (x, y, z, -)
     unsigned long long best[TC_TILE];            // per query (distance bits << 32) | original target index: its 64-bit minimum IS the first minimum
-    uint16_t queue[TC_QCAP];                     // (query row << 7) | chunk of the pass: candidates waiting for the box test + exact evaluation
-    uint64_t a_full, b_full[2], mma_done, t_full;
+    uint16_t queue[TC_QCAP];                     // (query row << 7) | chunk of the pass: candidates that passed the box test
+    uint64_t b_full[2], mma_done, t_full[2];
     uint32_t tmem_base;
     uint32_t big[4];                             // this pass's capped chunks (always box-tested)
     uint32_t qn;                                 // queue fill
+    float4 tail[1];                              // (aligned up to 256 bytes at run time) STAGED: box[256] + tgt[2048];  streamed: box[2][256]
 };
+constexpr size_t TC_SMEM_STAGED = sizeof(SearchSmem) + 256 + (size_t)(TC_NC * 2 + TC_PASS_TARGETS) * 16;
+constexpr size_t TC_SMEM_STREAM = sizeof(SearchSmem) + 256 + (size_t)(2 * TC_NC * 2) * 16;
 
 // per lane (0x8000 | t) - v keeps bit 15 exactly when v <= t (both 15-bit values: no borrow crosses the lanes);
 // bits 15 / 31 of word i go to mask bits i / 16+i  -> bit u of m[g] <=> chunk 32 g + u of the pass
@@ -535,17 +537,26 @@ __device__ __forceinline__ void build_mask(const uint32_t* w, uint32_t t16, uint
     }
 }
 
+// a query's operand row, straight into the shared-memory tile (canonical K-major core-matrix layout)
+__device__ __forceinline__ void write_a_row_smem(unsigned char* tile, int r, float ux, float uy, float uz) {
+    write_a_row(tile, r, true, ux, uy, uz);
+}
+
+template <bool STAGED>
 __global__ void __launch_bounds__(TC_THREADS, 4)
 chamfer_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SearchSmem& S = *reinterpret_cast<SearchSmem*>(smem_raw);
+    // (256-byte aligned: the staged points' XOR-swizzled addressing needs chunk bases with eight zero low bits)
+    float4* const box_s = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(S.tail) + 255) & ~(uintptr_t)255);   // STAGED: one buffer; streamed: [2][256]
+    float4* const tgt_s = box_s + TC_NC * 2;                        // STAGED only
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int jobs_per_sample = p.tiles[0] + p.tiles[1];
     const int total_jobs = jobs_per_sample * p.B;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) mbar_init(&S.b_full[i], 1);
-        mbar_init(&S.a_full, 1); mbar_init(&S.mma_done, 1); mbar_init(&S.t_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&S.b_full[i], 1); mbar_init(&S.t_full[i], 1); }
+        mbar_init(&S.mma_done, 1);
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -560,62 +571,89 @@ chamfer_search_kernel(const SearchParams p) {
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     pdl_wait();                  // operands / metadata come from chamfer_sort_kernel
 
-    // decode a job id
     auto decode = [&](int job_id, int& b, int& dir, int& tile) {
         b = (int)((unsigned)job_id / (unsigned)jobs_per_sample);
         tile = job_id - b * jobs_per_sample;
         dir = tile < p.tiles[0] ? 0 : 1;
         if (dir) tile -= p.tiles[0];
     };
-    // thread 0: bulk loads of the MMA operands of step (job, pass) into the stage of its parities
-    auto issue_loads = [&](int job_id, int pass, uint32_t step, uint32_t jobn) {
+    // thread 0: the chunk-centre operand tile of step (job, pass)
+    auto issue_b = [&](int job_id, int pass, uint32_t step) {
         int b, dir, tile; decode(job_id, b, dir, tile);
         const int tgt = 1 - dir;
-        if (pass == 0) {          // (single buffer: the caller issues this only after the previous job's last MMA has completed)
-            mbar_expect_tx(&S.a_full, TC_TILE_BYTES);
-            bulk_g2s(S.a_tile, p.A[dir] + ((size_t)b * p.n_pad[dir] + (size_t)tile * TC_TILE) * 32, TC_TILE_BYTES, &S.a_full);
-        }
         mbar_expect_tx(&S.b_full[step & 1], TC_TILE_BYTES);
         bulk_g2s(S.b_tile[step & 1], p.Bc[tgt] + ((size_t)b * p.nc_pad[tgt] + (size_t)pass * TC_NC) * 32, TC_TILE_BYTES, &S.b_full[step & 1]);
     };
-    // thread 0: this pass's chunk boxes and sorted targets (one stage: issued once every thread is done with the previous pass)
-    auto issue_targets = [&](int job_id, int pass) {
+    // thread 0: this pass's chunk boxes (+ the whole sorted cloud when STAGED)
+    auto issue_t = [&](int job_id, int pass, uint32_t step) {
         int b, dir, tile; decode(job_id, b, dir, tile);
         const int tgt = 1 - dir;
-        mbar_expect_tx(&S.t_full, (uint32_t)(sizeof(S.box) + sizeof(S.tgt)));
-        bulk_g2s(S.box, p.box[tgt] + ((size_t)b * p.nc_pad[tgt] + (size_t)pass * TC_NC) * 2, (uint32_t)sizeof(S.box), &S.t_full);
-        bulk_g2s(S.tgt, p.S[tgt] + (size_t)b * p.nc_pad[tgt] * TC_CHUNK + (size_t)pass * TC_PASS_TARGETS, (uint32_t)sizeof(S.tgt), &S.t_full);
+        const int sl = STAGED ? 0 : (int)(step & 1);
+        const uint32_t box_bytes = TC_NC * 2 * 16, tgt_bytes = STAGED ? TC_PASS_TARGETS * 16 : 0;
+        mbar_expect_tx(&S.t_full[sl], box_bytes + tgt_bytes);
+        bulk_g2s(box_s + sl * TC_NC * 2, p.box[tgt] + ((size_t)b * p.nc_pad[tgt] + (size_t)pass * TC_NC) * 2, box_bytes, &S.t_full[sl]);
+        if (STAGED) bulk_g2s(tgt_s, p.S[tgt] + (size_t)b * p.nc_pad[tgt] * TC_CHUNK + (size_t)pass * TC_PASS_TARGETS, tgt_bytes, &S.t_full[sl]);
     };
-    auto issue_mma = [&](uint32_t step, uint32_t jobn, bool first_pass) {
-        if (first_pass) mbar_wait(&S.a_full, jobn & 1);
+    auto issue_mma = [&](uint32_t step) {
         mbar_wait(&S.b_full[step & 1], (step >> 1) & 1);
         tc_fence_after();
         umma_f16(tmem_base, umma_smem_desc(S.a_tile), umma_smem_desc(S.b_tile[step & 1]), TC_IDESC);
         umma_commit(&S.mma_done);
     };
     // the step after (job, pass) of this CTA's static job list; false when there is none
-    auto next_step = [&](int& job_id, int& pass, uint32_t& jobn) -> bool {
+    auto next_step = [&](int& job_id, int& pass) -> bool {
         int b, dir, tile; decode(job_id, b, dir, tile);
         const int passes = p.nc_pad[1 - dir] / TC_NC;
         if (pass + 1 < passes) { ++pass; return true; }
-        job_id += gridDim.x; pass = 0; ++jobn;
+        job_id += gridDim.x; pass = 0;
         return job_id < total_jobs;
     };
+    // a job's query of this thread, in the SORTED order of its cloud: the 128 queries of a tile are neighbours, so they test and
+    // evaluate the same few chunks (measured with queries in original order: 46 vs 36 us at 32 x 2048^2, 297 vs 164 us at
+    // 8192^2 -- scattered box / chunk reads).  Non-finite samples are not sorted: original order.
+    auto load_query = [&](int job_id, float& x, float& y, float& z, int& orig) {
+        x = y = z = 0.f; orig = 0;
+        if (job_id < total_jobs) {
+            int b, dir, tile; decode(job_id, b, dir, tile);
+            const int row = tile * TC_TILE + tid;
+            if (row < p.n[dir]) {
+                if (__ldg(&p.meta[b].nonfinite) != 0.f) {
+                    const float* q = p.xyz[dir] + ((size_t)b * p.n[dir] + row) * 3;
+                    x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2); orig = row;
+                } else {
+                    const float4 q = __ldg(p.S[dir] + (size_t)b * p.nc_pad[dir] * TC_CHUNK + row);
+                    x = q.x; y = q.y; z = q.z; orig = __float_as_int(q.w);
+                }
+            }
+        }
+    };
+    // every thread: its query's operand row of job `job_id` into the (free) query tile
+    auto format_a = [&](int job_id, float x, float y, float z) {
+        int b, dir, tile; decode(job_id, b, dir, tile);
+        const ChamferMeta mt = p.meta[b];
+        const bool live = tile * TC_TILE + tid < p.n[dir];
+        write_a_row(S.a_tile, tid, live, (x - mt.cx) * mt.scale, (y - mt.cy) * mt.scale, (z - mt.cz) * mt.scale);
+        fence_proxy_async_smem();                                    // generic-proxy writes -> visible to the MMA's operand reads
+    };
 
-    // producer state (thread 0 only): the step whose operand loads / MMA are issued next
-    int ld_job = blockIdx.x, ld_pass = 0; uint32_t ld_step = 0, ld_jobn = 0; bool ld_valid = ld_job < total_jobs;
-    int mm_job = blockIdx.x, mm_pass = 0; uint32_t mm_step = 0, mm_jobn = 0; bool mm_valid = mm_job < total_jobs;
-    if (tid == 0 && ld_valid) {
-        issue_targets(ld_job, 0);
-        issue_loads(ld_job, ld_pass, ld_step, ld_jobn);
-        ld_valid = next_step(ld_job, ld_pass, ld_jobn); ++ld_step;
-        if (ld_valid && ld_pass != 0) { issue_loads(ld_job, ld_pass, ld_step, ld_jobn); ld_valid = next_step(ld_job, ld_pass, ld_jobn); ++ld_step; }
-        issue_mma(mm_step, mm_jobn, true);
-        mm_valid = next_step(mm_job, mm_pass, mm_jobn); ++mm_step;
+    // producer state (thread 0): the next step whose chunk-centre tile is loaded / whose boxes are loaded
+    int ld_job = blockIdx.x, ld_pass = 0; uint32_t ld_step = 0; bool ld_valid = ld_job < total_jobs;
+    int tl_job = blockIdx.x, tl_pass = 0; uint32_t tl_step = 0; bool tl_valid = tl_job < total_jobs;
+    float nqx, nqy, nqz; int nqo;                                    // this thread's query of the NEXT job (prefetched)
+    load_query(blockIdx.x, nqx, nqy, nqz, nqo);
+    if (ld_valid) {
+        if (tid == 0) {
+            issue_t(tl_job, tl_pass, tl_step); tl_valid = next_step(tl_job, tl_pass); ++tl_step;
+            if (!STAGED && tl_valid) { issue_t(tl_job, tl_pass, tl_step); tl_valid = next_step(tl_job, tl_pass); ++tl_step; }
+            for (int i = 0; i < 2 && ld_valid; ++i) { issue_b(ld_job, ld_pass, ld_step); ld_valid = next_step(ld_job, ld_pass); ++ld_step; }
+        }
+        format_a(blockIdx.x, nqx, nqy, nqz);
+        __syncthreads();
+        if (tid == 0) issue_mma(0);
     }
 
-    uint32_t step = 0, cur_jobn = 0;
-    for (int job_id = blockIdx.x; job_id < total_jobs; job_id += gridDim.x, ++cur_jobn) {
+    uint32_t step = 0;
+    for (int job_id = blockIdx.x; job_id < total_jobs; job_id += gridDim.x) {
         int b, dir, tile; decode(job_id, b, dir, tile);
         const int tgt = 1 - dir;
         const int nq = p.n[dir], nt = p.n[tgt];
@@ -623,25 +661,61 @@ chamfer_search_kernel(const SearchParams p) {
         const ChamferMeta mt = p.meta[b];
         const bool eval_all = mt.nonfinite != 0.f;
         const float* Tx = p.xyz[tgt] + (size_t)b * nt * 3;
-        const int row = tile * TC_TILE + tid;                       // position in the SORTED query cloud
-        // query: sorted order (neighbouring lanes are neighbouring points); non-finite samples are not sorted
-        float qx = 0.f, qy = 0.f, qz = 0.f; int qorig = row;
+        const float4* Sg = p.S[tgt] + (size_t)b * p.nc_pad[tgt] * TC_CHUNK;     // sorted targets (global)
+        const int row = tile * TC_TILE + tid;                       // position in the sorted query cloud
         const bool live = row < nq;
-        if (live) {
-            if (eval_all) {
-                const float* q = p.xyz[dir] + ((size_t)b * nq + row) * 3;
-                qx = __ldg(q); qy = __ldg(q + 1); qz = __ldg(q + 2);
-            } else {
-                const float4 q = __ldg(p.S[dir] + (size_t)b * p.nc_pad[dir] * TC_CHUNK + row);
-                qx = q.x; qy = q.y; qz = q.z; qorig = __float_as_int(q.w);
-            }
-        }
+        const float qx = nqx, qy = nqy, qz = nqz;
+        const int qorig = nqo;
+        load_query(job_id + gridDim.x, nqx, nqy, nqz, nqo);         // the next job's query: in registers long before it is needed
         // reference: the first target initialises the running best (`k==0 || d<best`, chamfer.cu:36)
         float best_d = ref_sqdist_tc(qx, qy, qz, __ldg(Tx), __ldg(Tx + 1), __ldg(Tx + 2));
         int best_i = 0;
         if (eval_all && live) ref_order_nn(Tx, nt, qx, qy, qz, best_d, best_i);
         // first minimum: smaller distance, or equal distance at a lower original index
         auto take = [&](float dmin, int imin) { if (dmin < best_d || (dmin == best_d && imin < best_i)) { best_d = dmin; best_i = imin; } };
+        // the 16 points of a chunk against query (x, y, z): minimum distance and the lowest original index that attains it.
+        // Shared memory (STAGED): every chunk starts on a 256-byte boundary, so the visiting order is XOR-swizzled by the lane
+        // and the lanes of a quarter-warp hit different banks (one LOP3 per address).  Global memory otherwise.
+        auto chunk_min = [&](bool in_smem, int jl, int jg, float x, float y, float z, float bound, float& dmin, int& imin) {
+            float dv[TC_CHUNK];
+            imin = 0x7FFFFFFF;
+            if (in_smem) {
+                const uint32_t base = smem_u32(tgt_s + jl * TC_CHUNK) | ((uint32_t)(lane & 15) << 4);
+#pragma unroll
+                for (int k = 0; k < TC_CHUNK; ++k) {
+                    float tx, ty, tz, tw;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tx), "=f"(ty), "=f"(tz), "=f"(tw) : "r"(base ^ (uint32_t)(k << 4)));
+                    (void)tw;
+                    dv[k] = ref_sqdist_tc(x, y, z, tx, ty, tz);      // padding points are +inf: never the minimum
+                }
+                dmin = min16(dv);
+                if (dmin <= bound) {
+                    // which points attain the minimum: almost always one -> one more shared-memory read for its original index
+                    uint32_t eq = 0;
+#pragma unroll
+                    for (int k = 0; k < TC_CHUNK; ++k) eq |= (dv[k] == dmin) ? (1u << k) : 0u;
+                    while (eq) {
+                        const int k = __ffs((int)eq) - 1;
+                        eq &= eq - 1;
+                        int iw;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(iw) : "r"((base ^ (uint32_t)(k << 4)) + 12u));
+                        imin = min(imin, iw);
+                    }
+                }
+            } else {
+                const float4* tg = Sg + (size_t)jg * TC_CHUNK;
+#pragma unroll
+                for (int k = 0; k < TC_CHUNK; ++k) { const float4 t = __ldg(tg + k); dv[k] = ref_sqdist_tc(x, y, z, t.x, t.y, t.z); }
+                dmin = min16(dv);
+                if (dmin <= bound) {
+                    uint32_t eq = 0;
+#pragma unroll
+                    for (int k = 0; k < TC_CHUNK; ++k) eq |= (dv[k] == dmin) ? (1u << k) : 0u;
+                    while (eq) { const int k = __ffs((int)eq) - 1; eq &= eq - 1; imin = min(imin, __float_as_int(__ldg(&tg[k].w))); }
+                }
+            }
+            TC_COUNT(4, 1);
+        };
         float tbias = 0.f;                                          // bias of the target cloud's chunk rows
         int home = 0;                                               // chunk of the query's own cell in the target cloud's grid
         if (!eval_all && live) {
@@ -649,61 +723,17 @@ chamfer_search_kernel(const SearchParams p) {
             const uint32_t code = hilbert_code((uint32_t)cell_of(qx, gi.lo[0], gi.inv[0]), (uint32_t)cell_of(qy, gi.lo[1], gi.inv[1]), (uint32_t)cell_of(qz, gi.lo[2], gi.inv[2]));
             tbias = gi.bias;
             home = min((int)__ldg(p.cellstart[tgt] + (size_t)b * SORT_CELLS + code), nt - 1) >> 4;
-            if (passes > 1) {
-                // a good first bound before the first pass: the points around the query's own cell (global memory; with one
-                // pass the whole cloud is in shared memory and the home chunk is evaluated from there)
-                const float4* tg = p.S[tgt] + (size_t)b * p.nc_pad[tgt] * TC_CHUNK + (size_t)home * TC_CHUNK;
-                float dv[TC_CHUNK];
-#pragma unroll
-                for (int k = 0; k < TC_CHUNK; ++k) { const float4 t = __ldg(tg + k); dv[k] = ref_sqdist_tc(qx, qy, qz, t.x, t.y, t.z); }
-                const float dmin = min16(dv);
-                int imin = 0x7FFFFFFF;
-#pragma unroll
-                for (int k = 0; k < TC_CHUNK; ++k) imin = min(imin, dv[k] == dmin ? __float_as_int(__ldg(&tg[k].w)) : 0x7FFFFFFF);
-                take(dmin, imin);
+            if (!STAGED || passes > 1) {   // a good first bound before the first pass: the points around the query's own cell (global memory)
+                float dmin; int imin;
+                chunk_min(false, 0, home, qx, qy, qz, best_d, dmin, imin);
+                if (dmin <= best_d) take(dmin, imin);
             }
         }
-        // the 16 points of chunk jl of the pass (shared memory) against query (x, y, z): minimum distance and the lowest original
-        // index that attains it.  Every chunk starts on a 256-byte boundary: the visiting order is XOR-swizzled by the lane so that
-        // the lanes of a quarter-warp hit different banks (one LOP3 per address).
-        auto chunk_min = [&](int jl, float x, float y, float z, float bound, float& dmin, int& imin) {
-            const uint32_t base = smem_u32(S.tgt + jl * TC_CHUNK) | ((uint32_t)(lane & 15) << 4);
-            float dv[TC_CHUNK];
-#pragma unroll
-            for (int k = 0; k < TC_CHUNK; ++k) {
-                float tx, ty, tz, tw;
-                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tx), "=f"(ty), "=f"(tz), "=f"(tw) : "r"(base ^ (uint32_t)(k << 4)));
-                dv[k] = ref_sqdist_tc(x, y, z, tx, ty, tz);          // padding points are +inf: never the minimum
-            }
-            dmin = min16(dv);
-            imin = 0x7FFFFFFF;
-            if (dmin <= bound) {
-                // which points attain the minimum: almost always one -> one more shared-memory read for its original index
-                uint32_t eq = 0;
-#pragma unroll
-                for (int k = 0; k < TC_CHUNK; ++k) eq |= (dv[k] == dmin) ? (1u << k) : 0u;
-                while (eq) {
-                    const int k = __ffs((int)eq) - 1;
-                    eq &= eq - 1;
-                    int iw;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(iw) : "r"((base ^ (uint32_t)(k << 4)) + 12u));
-                    imin = min(imin, iw);
-                }
-            }
-            TC_COUNT(4, 1);
-        };
-        // a queued candidate (it passed the box test of its query): the chunk's points; the result merges through a 64-bit
-        // shared-memory minimum -- distances are >= +0, so their bit patterns order like the values and the index breaks ties
-        auto run_item = [&](uint32_t item) {
-            const int r = (int)(item >> 7), jl = (int)(item & 127u);
-            const float4 q = S.q4[r];
-            const float bd = __uint_as_float((uint32_t)(S.best[r] >> 32));
-            float dmin; int imin;
-            chunk_min(jl, q.x, q.y, q.z, bd, dmin, imin);
-            if (dmin <= bd) atomicMin(&S.best[r], ((unsigned long long)__float_as_uint(dmin) << 32) | (unsigned)imin);
-        };
 
         for (int pass = 0; pass < passes; ++pass, ++step) {
+            const bool last_pass = pass == passes - 1;
+            const int sl = STAGED ? 0 : (int)(step & 1);
+            const float4* box_p = box_s + sl * TC_NC * 2;
             uint32_t w[64];                                        // 128 fp16 values V_j, two per register
             mbar_wait(&S.mma_done, step & 1);
             tc_fence_after();
@@ -711,29 +741,25 @@ chamfer_search_kernel(const SearchParams p) {
             for (int g = 0; g < 4; ++g) tmem_ld16p(lane_addr + 32 * g, w + 16 * g);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_wait(&S.t_full, step & 1);                        // this pass's boxes and targets have landed
+            mbar_wait(&S.t_full[sl], STAGED ? (step & 1) : ((step >> 1) & 1));     // this pass's boxes (and targets) have landed
             {   // this pass's capped chunks (one flag per thread -> four ballot words)
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, S.box[2 * tid].w != 0.f);
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, box_p[2 * tid].w != 0.f);
                 if (lane == 0) S.big[warp] = bal;
             }
             if (tid == 0) S.qn = 0;
             __syncthreads();                                       // accumulator in registers everywhere: TMEM and the operand stages are free
-            // Producer (thread 0).  Operand loads run up to two steps ahead, but the single query-tile buffer may only be
-            // refilled once this job's last MMA (the one just drained) is done; the next job's first MMA is then issued
-            // after the enqueue phase below, when that tile has had time to land.
-            bool mma_late = false;
             if (tid == 0) {
-                if (mm_valid) { if (mm_pass != 0) { issue_mma(mm_step, mm_jobn, false); mm_valid = next_step(mm_job, mm_pass, mm_jobn); ++mm_step; } else mma_late = true; }
-                while (ld_valid && ld_step <= step + 2 && (ld_pass != 0 || (pass == passes - 1 && ld_jobn == cur_jobn + 1))) {
-                    issue_loads(ld_job, ld_pass, ld_step, ld_jobn); ld_valid = next_step(ld_job, ld_pass, ld_jobn); ++ld_step;
-                }
+                // the next pass of this job can go at once (same query tile); the next JOB's first MMA waits for its query tile,
+                // which the CTA writes at the end of this pass
+                if (!last_pass) issue_mma(step + 1);
+                while (ld_valid && ld_step <= step + 2) { issue_b(ld_job, ld_pass, ld_step); ld_valid = next_step(ld_job, ld_pass); ++ld_step; }
             }
             const bool act = !eval_all && live;
             uint32_t over[4] = {0u, 0u, 0u, 0u};
             if (act) {
-                if (passes == 1) {                                   // a good first bound: the points around the query's own cell
+                if (STAGED && passes == 1) {                         // a good first bound: the points around the query's own cell
                     float dmin; int imin;
-                    chunk_min(home, qx, qy, qz, best_d, dmin, imin);
+                    chunk_min(true, home, home, qx, qy, qz, best_d, dmin, imin);
                     if (dmin <= best_d) take(dmin, imin);
                 }
                 S.q4[tid] = make_float4(qx, qy, qz, 0.f);
@@ -746,21 +772,20 @@ chamfer_search_kernel(const SearchParams p) {
                 uint32_t m[4];
                 build_mask(w, t16, m);
                 TC_COUNT(0, 1); TC_COUNT(2, __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]));
-                // ---- candidates -> queue (a thread whose candidates do not fit evaluates them itself, after the barrier) ----
+                // ---- box test (float32, this query's best so far); survivors go to the queue -------------------------------
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint32_t mm = m[g] | S.big[g];
-                    if (pass == passes - 1) {                        // chunks past the cloud's end (only reachable when best is +inf)
+                    if (last_pass) {                                 // chunks past the cloud's end (only reachable when best is +inf)
                         const int lim = nc_t - pass * TC_NC - g * 32;
                         mm &= lim >= 32 ? 0xFFFFFFFFu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
                     }
-                    // box test (float32, this query's best so far); survivors go to the queue
                     uint32_t pass_bits = 0;
                     while (mm) {
                         const int bit = __ffs((int)mm) - 1;
                         mm &= mm - 1;
                         const int jl = g * 32 + bit;
-                        const float4 lo = S.box[2 * jl], hi = S.box[2 * jl + 1];
+                        const float4 lo = box_p[2 * jl], hi = box_p[2 * jl + 1];
                         const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.f), dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.f),
                                     dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.f);
                         const float d2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
@@ -777,10 +802,19 @@ chamfer_search_kernel(const SearchParams p) {
                     }
                 }
             }
-            if (mma_late) { issue_mma(mm_step, mm_jobn, true); mm_valid = next_step(mm_job, mm_pass, mm_jobn); ++mm_step; }
             __syncthreads();
             if (!eval_all) {
-                // ---- every thread takes queued candidates round-robin: balanced whatever the per-query counts are ----
+                // ---- every thread takes queued candidates round-robin: balanced whatever the per-query counts are.  The result
+                // merges through a 64-bit shared-memory minimum: distances are >= +0, so their bit patterns order like the values
+                // and the original index breaks ties downwards.
+                auto run_item = [&](uint32_t item) {
+                    const int r = (int)(item >> 7), jl = (int)(item & 127u);
+                    const float4 q = S.q4[r];
+                    const float bd = __uint_as_float((uint32_t)(S.best[r] >> 32));
+                    float dmin; int imin;
+                    chunk_min(STAGED, jl, pass * TC_NC + jl, q.x, q.y, q.z, bd, dmin, imin);
+                    if (dmin <= bd) atomicMin(&S.best[r], ((unsigned long long)__float_as_uint(dmin) << 32) | (unsigned)imin);
+                };
                 const uint32_t total = min(S.qn, (uint32_t)TC_QCAP);
                 for (uint32_t it = tid; it < total; it += TC_THREADS) run_item(S.queue[it]);
 #pragma unroll
@@ -789,14 +823,17 @@ chamfer_search_kernel(const SearchParams p) {
                     while (mm) { const int bit = __ffs((int)mm) - 1; mm &= mm - 1; run_item((uint32_t)((tid << 7) | (g * 32 + bit))); }
                 }
             }
+            // the next job's query tile: this job's last MMA is long done, the tile is free
+            if (last_pass && job_id + (int)gridDim.x < total_jobs) format_a(job_id + gridDim.x, nqx, nqy, nqz);
             __syncthreads();                                       // every thread is done with this pass's boxes / targets / queue
             if (act) {
                 const unsigned long long v = S.best[tid];
                 best_d = __uint_as_float((uint32_t)(v >> 32)); best_i = (int)(uint32_t)v;
             }
             if (tid == 0) {
-                int nj = job_id, np_ = pass; uint32_t dummy = 0;
-                if (next_step(nj, np_, dummy)) issue_targets(nj, np_);
+                if (last_pass && job_id + (int)gridDim.x < total_jobs) issue_mma(step + 1);
+                // boxes (+ targets): STAGED has one buffer, refilled now; streamed boxes run one pass ahead in the other buffer
+                while (tl_valid && tl_step <= step + (STAGED ? 1u : 2u)) { issue_t(tl_job, tl_pass, tl_step); tl_valid = next_step(tl_job, tl_pass); ++tl_step; }
             }
         }
         if (p.loss != nullptr) {
@@ -824,7 +861,7 @@ static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 struct TcLayout {
     int n_pad[2], nc[2], nc_pad[2];
-    size_t off_meta, off_S[2], off_A[2], off_Bc[2], off_box[2], off_cs[2], off_grid[2], total;
+    size_t off_meta, off_S[2], off_Bc[2], off_box[2], off_cs[2], off_grid[2], total;
 };
 static TcLayout tc_layout(int B, int n, int m) {
     TcLayout L;
@@ -836,7 +873,6 @@ static TcLayout tc_layout(int B, int n, int m) {
         L.nc[c] = (cnt[c] + TC_CHUNK - 1) / TC_CHUNK;
         L.nc_pad[c] = (int)round_up((size_t)L.nc[c], TC_NC);
         L.off_S[c] = o; o += round_up((size_t)B * L.nc_pad[c] * TC_CHUNK * 16, 256);     // whole passes: a pass is one bulk copy
-        L.off_A[c] = o; o += round_up((size_t)B * L.n_pad[c] * 32, 256);
         L.off_Bc[c] = o; o += round_up((size_t)B * L.nc_pad[c] * 32, 256);
         L.off_box[c] = o; o += round_up((size_t)B * L.nc_pad[c] * 32, 256);
         L.off_cs[c] = o; o += round_up((size_t)B * SORT_CELLS * 2, 256);
@@ -865,12 +901,12 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
     for (int c = 0; c < 2; ++c) {
         sp.xyz[c] = xyz[c]; sp.n[c] = cnt[c]; sp.n_pad[c] = L.n_pad[c]; sp.nc[c] = L.nc[c]; sp.nc_pad[c] = L.nc_pad[c];
         sp.S[c] = reinterpret_cast<float4*>(base + L.off_S[c]);
-        sp.A[c] = base + L.off_A[c]; sp.Bc[c] = base + L.off_Bc[c];
+        sp.Bc[c] = base + L.off_Bc[c];
         sp.box[c] = reinterpret_cast<float4*>(base + L.off_box[c]);
         sp.cellstart[c] = reinterpret_cast<uint16_t*>(base + L.off_cs[c]);
         sp.grid[c] = reinterpret_cast<ChamferGrid*>(base + L.off_grid[c]);
         qp.xyz[c] = xyz[c]; qp.n[c] = cnt[c]; qp.n_pad[c] = L.n_pad[c]; qp.nc[c] = L.nc[c]; qp.nc_pad[c] = L.nc_pad[c];
-        qp.S[c] = sp.S[c]; qp.A[c] = sp.A[c]; qp.Bc[c] = sp.Bc[c]; qp.box[c] = sp.box[c];
+        qp.S[c] = sp.S[c]; qp.Bc[c] = sp.Bc[c]; qp.box[c] = sp.box[c];
         qp.cellstart[c] = sp.cellstart[c]; qp.grid[c] = sp.grid[c];
         qp.tiles[c] = (cnt[c] + TC_TILE - 1) / TC_TILE;
     }
@@ -894,15 +930,20 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
     }
     SPK_CUDA(launch_k(chamfer_sort_kernel, dim3(2, B), dim3(SORT_THREADS), sort_smem, st, sp));
 
-    // dynamic shared memory sized so that at most 4 CTAs share an SM (each owns 128 of the 512 TMEM columns)
-    const size_t smem = std::max(sizeof(SearchSmem) + 128, (size_t)50 * 1024);
+    // dynamic shared memory of at least 50 KB, so that at most 4 CTAs share an SM (each owns 128 of the 512 TMEM columns)
+    // every pass's boxes + sorted points are staged in shared memory (one buffer).  The streamed variant (boxes only, points
+    // from global memory / L2 when evaluated: chamfer_search_kernel<false>) was measured SLOWER: 192 vs 164 us at 32 x 8192^2.
+    const bool staged = true;
+    const size_t smem = std::max(staged ? TC_SMEM_STAGED : TC_SMEM_STREAM, (size_t)50 * 1024);
     if (!search_attr[dslot] || dev != dslot) {
-        SPK_CUDA(cudaFuncSetAttribute(chamfer_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SPK_CUDA(cudaFuncSetAttribute(chamfer_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(TC_SMEM_STAGED, (size_t)50 * 1024)));
+        SPK_CUDA(cudaFuncSetAttribute(chamfer_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(TC_SMEM_STREAM, (size_t)50 * 1024)));
         search_attr[dslot] = true;
     }
     const long long jobs = (long long)(qp.tiles[0] + qp.tiles[1]) * B;
     const int grid = (int)std::min<long long>(jobs, 4LL * sm_count());
-    SPK_CUDA(launch_k(chamfer_search_kernel, dim3(grid), dim3(TC_THREADS), smem, st, qp));
+    if (staged) SPK_CUDA(launch_k(chamfer_search_kernel<true>, dim3(grid), dim3(TC_THREADS), smem, st, qp));
+    else SPK_CUDA(launch_k(chamfer_search_kernel<false>, dim3(grid), dim3(TC_THREADS), smem, st, qp));
     return SPK_OK;
 }
 
