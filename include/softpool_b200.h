@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SPK_ABI_VERSION 2   /* 2: + chamfer_fwd_loss_f32 */
+#define SPK_ABI_VERSION 3   /* 2: + chamfer_fwd_loss_f32; 3: + chamfer_fwd_multi_f32 */
 
 enum {
     SPK_OK = 0,
@@ -138,6 +138,18 @@ int chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int n, int m, f
 int chamfer_fwd_loss_f32(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
                          float* dist2, int32_t* idx1, int32_t* idx2, float* loss, void* ws,
                          size_t ws_bytes, void* stream);
+
+/* P predictions against ONE ground truth in one call -- the training step's `self.CD(output1[i], gt)` for i = 1..3 and
+ * the `output2` pair (train.py:68-86), which the reference runs as P separate forward calls.
+ *   xyz1 (P*B, n, 3): the predictions stacked along the batch (prediction p, sample b at row p*B + b);
+ *   xyz2 (B, m, 3): the shared ground truth.  Outputs as chamfer_fwd_loss_f32 with batch P*B:
+ *   dist1/idx1 (P*B, n), dist2/idx2 (P*B, m), loss (P*B) or NULL.  Results are bit-identical to P separate calls.
+ *   On the dense tensor path this is ONE prep launch + ONE tensor launch, and the ground truth's operand rows are
+ *   formatted once per sample (all P predictions of a sample share one frame); other paths loop over p internally.
+ *   ws: chamfer_fwd_workspace_bytes(P*B, n, m).                                                                  */
+int chamfer_fwd_multi_f32(const float* xyz1, const float* xyz2, int P, int B, int n, int m, float* dist1,
+                          float* dist2, int32_t* idx1, int32_t* idx2, float* loss, void* ws,
+                          size_t ws_bytes, void* stream);
 
 /* Replaces `chamfer_cuda_backward` = 2 x NmDistanceGradKernel (chamfer.cu:155-196); one launch
  * (a thread-block cluster per sample: direct terms, cluster barrier, scatter terms).

@@ -9,7 +9,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsoftpool_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -28,6 +28,7 @@ _SIGS = {
     "chamfer_bwd_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "chamfer_loss_f32": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "chamfer_fwd_loss_f32": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, ctypes.c_size_t, _p]),
+    "chamfer_fwd_multi_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, ctypes.c_size_t, _p]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -288,7 +288,7 @@ static int chamfer_fwd_impl(const float* xyz1, const float* xyz2, int B, int n, 
     if (B > 65535) return fail(SPK_E_UNSUPPORTED, "%s: B=%d > 65535", who, B);
     const int path = chamfer_path(B, n, m);
     if (path == 2) return chamfer_tc_forward(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, loss, ws, ws_bytes, st);
-    if (path == 1) return chamfer_dense_forward(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, loss, ws, ws_bytes, st);
+    if (path == 1) return chamfer_dense_forward(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, loss, ws, ws_bytes, st, B);
     const int per = CH_THREADS * CH_QPT;
     dim3 grid((max(n, m) + per - 1) / per, B, 2);
     SPK_CUDA(launch_k(chamfer_nn_exact_kernel, grid, dim3(CH_THREADS), 0, st, xyz1, xyz2, n, m, dist1, dist2, idx1, idx2));
@@ -308,6 +308,26 @@ extern "C" int chamfer_fwd_loss_f32(const float* xyz1, const float* xyz2, int B,
                                     void* ws, size_t ws_bytes, void* stream) {
     if (!loss) return spk::fail(SPK_E_BADARG, "chamfer_fwd_loss_f32: null loss");
     return chamfer_fwd_impl(xyz1, xyz2, B, n, m, dist1, dist2, idx1, idx2, loss, ws, ws_bytes, stream, "chamfer_fwd_loss_f32");
+}
+
+extern "C" int chamfer_fwd_multi_f32(const float* xyz1, const float* xyz2, int P, int B, int n, int m,
+                                     float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* loss,
+                                     void* ws, size_t ws_bytes, void* stream) {
+    using namespace spk;
+    if (P < 1 || B < 0 || n < 1 || m < 1) return fail(SPK_E_BADARG, "chamfer_fwd_multi_f32: need P>=1, B>=0, n,m>=1");
+    if (B == 0) return SPK_OK;
+    if (!xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return fail(SPK_E_BADARG, "chamfer_fwd_multi_f32: null pointer");
+    if ((long long)P * B > 65535) return fail(SPK_E_UNSUPPORTED, "chamfer_fwd_multi_f32: P*B=%lld > 65535", (long long)P * B);
+    if (chamfer_path(P * B, n, m) == 1)        // dense tensor path: ONE prep + ONE tensor launch, the ground truth formatted once per sample
+        return chamfer_dense_forward(xyz1, xyz2, P * B, n, m, dist1, dist2, idx1, idx2, loss, ws, ws_bytes, (cudaStream_t)stream, B);
+    // small pair blocks (plain kernel) and large clouds (sorted search): one call per prediction on the same stream
+    for (int p = 0; p < P; ++p) {
+        const size_t o1 = (size_t)p * B * n, o2 = (size_t)p * B * m;
+        const int rc = chamfer_fwd_impl(xyz1 + o1 * 3, xyz2, B, n, m, dist1 + o1, dist2 + o2, idx1 + o1, idx2 + o2,
+                                        loss ? loss + (size_t)p * B : nullptr, ws, ws_bytes, stream, "chamfer_fwd_multi_f32");
+        if (rc != SPK_OK) return rc;
+    }
+    return SPK_OK;
 }
 
 extern "C" int chamfer_bwd_f32(const float* xyz1, const float* xyz2, const float* g1, const float* g2,

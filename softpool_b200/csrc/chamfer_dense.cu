@@ -132,6 +132,9 @@ struct PrepParams {
     unsigned long long* packed1; unsigned long long* packed2;   // split jobs only: (dist bits << 32 | idx) minima, B*n / B*m
     int* counters; int n_counters;   // split jobs only: arrivals per (sample, direction, query tile)
     float* loss;                     // fused loss only: (B) accumulators, zeroed here
+    int n_gt;                        // distinct xyz2 samples: sample b pairs xyz1[b] with xyz2[b % n_gt] (several predictions share one
+                                     // ground truth, train.py:68-86); n_gt == B for the plain call
+    int P;                           // predictions per ground truth = B / B2
 };
 
 __global__ void __launch_bounds__(256)
@@ -141,8 +144,10 @@ chamfer_prep_kernel(const PrepParams p) {
     pdl_trigger();
     pdl_wait();
     const int b = blockIdx.y, tid = threadIdx.x;
+    const int b2 = b % p.n_gt;                          // the ground-truth sample; its operands are written by prediction 0 only
+    const bool own_q = b < p.n_gt;
     const float* P = p.xyz1 + (size_t)b * p.n * 3;
-    const float* Q = p.xyz2 + (size_t)b * p.m * 3;
+    const float* Q = p.xyz2 + (size_t)b2 * p.m * 3;
     // this thread's own rows first (raw coordinates into registers): their trip to L2 / DRAM then overlaps the
     // bounding-box pass instead of following it
     constexpr int PRE = 2;
@@ -168,9 +173,11 @@ chamfer_prep_kernel(const PrepParams p) {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     int bad = 0;                                        // a NaN / inf coordinate anywhere in the sample
     auto upd = [&](int a, float v) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); bad |= !(fabsf(v) < INFINITY); };
-    for (int c = 0; c < 2; ++c) {
-        const float* X = c ? Q : P;
-        const int cnt = c ? p.m : p.n;
+    // (all predictions that share the ground truth share ONE frame -- centre, scale, bias -- so that the ground truth's
+    // operand rows are the same for each of them: the box runs over the ground truth and every prediction of sample b2)
+    for (int c = 0; c <= p.P; ++c) {
+        const float* X = c == p.P ? Q : p.xyz1 + ((size_t)c * p.n_gt + b2) * p.n * 3;
+        const int cnt = c == p.P ? p.m : p.n;
         int done = 0;
         if ((((uintptr_t)X) & 15) == 0) {
             const int steps = cnt / 4;                               // 4 points = 12 floats = 3 float4
@@ -235,7 +242,7 @@ chamfer_prep_kernel(const PrepParams p) {
     __syncthreads();
     const float cx = s_meta[0], cy = s_meta[1], cz = s_meta[2], sc = s_meta[3], bias = s_meta[6];
     unsigned char* A1 = p.A1 + (size_t)b * p.n_pad * 32; unsigned char* B1 = p.B1 + (size_t)b * p.n_pad * 32;
-    unsigned char* A2 = p.A2 + (size_t)b * p.m_pad * 32; unsigned char* B2 = p.B2 + (size_t)b * p.m_pad * 32;
+    unsigned char* A2 = p.A2 + (size_t)b2 * p.m_pad * 32; unsigned char* B2 = p.B2 + (size_t)b2 * p.m_pad * 32;
     const int total = p.n_pad + p.m_pad;
     int it_pre = 0;
     for (int i = blockIdx.x * 256 + tid; i < total; i += gridDim.x * 256, ++it_pre) {
@@ -251,8 +258,10 @@ chamfer_prep_kernel(const PrepParams p) {
             else { raw.x = __ldg(s); raw.y = __ldg(s + 1); raw.z = __ldg(s + 2); }
             ux = (raw.x - cx) * sc; uy = (raw.y - cy) * sc; uz = (raw.z - cz) * sc;
         }
-        write_rows(first ? A1 : A2, first ? B1 : B2, r, real, ux, uy, uz, bias);
-        (first ? p.T1 + (size_t)b * p.n_pad : p.T2 + (size_t)b * p.m_pad)[r] = raw;
+        if (first || own_q) {
+            write_rows(first ? A1 : A2, first ? B1 : B2, r, real, ux, uy, uz, bias);
+            (first ? p.T1 + (size_t)b * p.n_pad : p.T2 + (size_t)b2 * p.m_pad)[r] = raw;
+        }
         if (real && p.packed1 != nullptr)
             (first ? p.packed1 + (size_t)b * p.n : p.packed2 + (size_t)b * p.m)[r] = ~0ull;
     }
@@ -388,6 +397,7 @@ struct TcParams {
     int S1, S2;              // target-range splits per query tile in direction 0 / 1 (1 = whole range in one job)
     unsigned long long* packed1; unsigned long long* packed2; int* counters;    // merge of split jobs
     float* loss;             // fused loss (or NULL): (B) accumulators zeroed by the prep kernel
+    int n_gt;                // distinct xyz2 samples (sample b uses xyz2[b % n_gt]); n_gt == B for the plain call
 };
 
 struct __align__(128) TcSmem {
@@ -485,9 +495,10 @@ chamfer_tc_kernel(const TcParams p) {
         if (warp == 0) {
             // ===== TMA producer =====
             if (lane == 0) {
-                const unsigned char* Aop = (dir ? p.A2 : p.A1) + ((size_t)b * nq_pad + (size_t)job * TC_TILE) * 32;
-                const unsigned char* Bop = (dir ? p.B1 : p.B2) + ((size_t)b * nt_pad + (size_t)sb0 * TC_SB_TARGETS) * 32;
-                const float4* T4 = (dir ? p.T1 : p.T2) + (size_t)b * nt_pad + (size_t)sb0 * TC_SB_TARGETS;
+                const int b2 = b % p.n_gt, bq = dir ? b2 : b, bt = dir ? b : b2;     // cloud-2 arrays exist once per ground-truth sample
+                const unsigned char* Aop = (dir ? p.A2 : p.A1) + ((size_t)bq * nq_pad + (size_t)job * TC_TILE) * 32;
+                const unsigned char* Bop = (dir ? p.B1 : p.B2) + ((size_t)bt * nt_pad + (size_t)sb0 * TC_SB_TARGETS) * 32;
+                const float4* T4 = (dir ? p.T1 : p.T2) + (size_t)bt * nt_pad + (size_t)sb0 * TC_SB_TARGETS;
                 const uint32_t ab = job_it & 1;
                 mbar_wait(&S.a_empty[ab], (uint32_t)(((job_it >> 1) & 1) ^ 1));   // the job two back has read this buffer
                 mbar_expect_tx(&S.a_full[ab], TC_TILE_BYTES);
@@ -589,8 +600,9 @@ chamfer_tc_kernel(const TcParams p) {
             const int row = q * 32 + lane;                         // query row inside the tile
             const int gq = job * TC_TILE + row;                    // query index inside the cloud
             const bool live = gq < nq;
-            const float* Qx = (dir ? p.xyz2 : p.xyz1) + (size_t)b * nq * 3;
-            const float* Tx = (dir ? p.xyz1 : p.xyz2) + (size_t)b * nt * 3;
+            const int b2 = b % p.n_gt;
+            const float* Qx = (dir ? p.xyz2 + (size_t)b2 * nq * 3 : p.xyz1 + (size_t)b * nq * 3);
+            const float* Tx = (dir ? p.xyz1 + (size_t)b * nt * 3 : p.xyz2 + (size_t)b2 * nt * 3);
             const ChamferMeta mt = p.meta[b];
             const float tau = mt.tau, scale2 = mt.scale2, bias = mt.bias;
             const bool eval_all = mt.nonfinite != 0.f;
@@ -763,7 +775,8 @@ size_t chamfer_dense_workspace_bytes(int B, int n, int m) {
 
 int chamfer_dense_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
                        float* dist2, int32_t* idx1, int32_t* idx2, float* loss, void* ws, size_t ws_bytes,
-                       cudaStream_t st) {
+                       cudaStream_t st, int B2) {
+    if (B2 < 1 || B % B2 != 0) return fail(SPK_E_BADARG, "chamfer forward: %d samples do not divide into ground truths of %d", B, B2);
     if (ws_bytes < chamfer_dense_workspace_bytes(B, n, m) || ws == nullptr)
         return fail(SPK_E_WORKSPACE, "chamfer_fwd_f32: workspace of %zu bytes needed, %zu given", chamfer_dense_workspace_bytes(B, n, m), ws_bytes);
     if (((uintptr_t)ws & 15) != 0) return fail(SPK_E_ALIGN, "chamfer_fwd_f32: workspace must be 16-byte aligned");
@@ -806,7 +819,7 @@ int chamfer_dense_forward(const float* xyz1, const float* xyz2, int B, int n, in
         pp.packed2 = pp.packed1 + (size_t)B * n;
         pp.counters = reinterpret_cast<int*>(pp.packed2 + (size_t)B * m);
     }
-    pp.loss = loss;
+    pp.loss = loss; pp.n_gt = B2; pp.P = B / B2;
     const int slices = std::max(1, std::min(16, (n_pad + m_pad) / 512));
     SPK_CUDA(launch_k(chamfer_prep_kernel, dim3(slices, B), dim3(256), 0, st, pp));
 
@@ -816,7 +829,7 @@ int chamfer_dense_forward(const float* xyz1, const float* xyz2, int B, int n, in
     tp.n = n; tp.m = m; tp.n_pad = n_pad; tp.m_pad = m_pad;
     tp.tiles1 = tiles1; tp.tiles2 = tiles2; tp.S1 = S1; tp.S2 = S2;
     tp.packed1 = pp.packed1; tp.packed2 = pp.packed2; tp.counters = pp.counters;
-    tp.loss = loss;
+    tp.loss = loss; tp.n_gt = B2;
     // request enough shared memory that at most 2 CTAs share an SM (each owns 256 of the 512 TMEM columns)
     const size_t smem = std::max(sizeof(TcSmem) + 128, (size_t)80 * 1024);
     SPK_CUDA(cudaFuncSetAttribute(chamfer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

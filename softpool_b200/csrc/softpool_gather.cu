@@ -232,6 +232,28 @@ __global__ void sp_cabins_generic_kernel(const float* __restrict__ sp_cube, int 
     pdl_wait();
     const int wl = k / cab;
     const long long total = n_rows * cab;
+    if (wl >= 32) {
+        // long windows (e.g. N = 16384: 256 slots): a WARP per window -- coalesced reads, the greatest key and then the
+        // lowest offset holding it by shuffles (one thread per window walked 256 strided floats: 500 us at N = 16384)
+        const int lane = threadIdx.x & 31;
+        const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+        for (long long t = warp0; t < total; t += nwarp) {
+            const long long rowi = t / cab;
+            const int w = (int)(t - rowi * cab);
+            const float* src = sp_cube + rowi * k + (size_t)w * wl;
+            uint32_t bk = 0; int bo = 0x7FFFFFFF;
+            for (int j = lane; j < wl; j += 32) {
+                const uint32_t kk = order_key(src[j]);
+                if (kk > bk || bo == 0x7FFFFFFF) { bk = kk; bo = j; }     // strict: the first maximum of this lane's slots
+            }
+            uint32_t kmax = bk;
+            for (int d = 16; d > 0; d >>= 1) kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, d));
+            int off = (bk == kmax) ? bo : 0x7FFFFFFF;
+            for (int d = 16; d > 0; d >>= 1) off = min(off, __shfl_xor_sync(0xFFFFFFFFu, off, d));
+            if (lane == 0) { cabins[t] = src[off]; cab_arg[t] = (uint16_t)off; }      // the value itself (sign of zero, NaN payload) from the winning slot
+        }
+        return;
+    }
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         const long long rowi = t / cab;
@@ -759,6 +781,9 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
     while (T > 1 && fixed + 2 * (size_t)T * row_bytes > budget) --T;
     T = std::min(T, C);
     p.T = T;
+    // rows so long that only ONE CTA fits an SM (two row buffers + index list > half the shared memory, e.g. N = 16384):
+    // a 1024-thread CTA keeps the SM busy (no measurable difference at N = 16384 once the window max ran a warp per window; kept for the long-row case)
+    if (fixed + 2 * (size_t)T * row_bytes > (size_t)110 * 1024) threads = 1024;
     // the per-group hoisting only pays when a tile holds several rows (measured: N=2048 33 vs 34.5 us; one row per tile, N=8192: 169 vs 145 us)
     p.q_cols = T >= 2 && p.vec4 && ((RK >> 2) % threads) == 0 && (!want_cab || p.cab_fast) && !tune_env("SPK_FWD_NO_QCOLS");
     const size_t smem = fixed + 2 * (size_t)T * row_bytes;
@@ -770,12 +795,13 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
         SPK_CUDA(launch_k(kern, dim3((int)grid), dim3(nt), smem, (cudaStream_t)stream, p));
         return SPK_OK;
     };
-    const int rc = threads == 128 ? launch(sp_gather_fwd_kernel<128>, 128) : launch(sp_gather_fwd_kernel<256>, 256);
+    const int rc = threads == 128 ? launch(sp_gather_fwd_kernel<128>, 128) : threads == 1024 ? launch(sp_gather_fwd_kernel<1024>, 1024) : launch(sp_gather_fwd_kernel<256>, 256);
     if (rc != SPK_OK) return rc;
     if (want_cab && !p.cab_fast) {
         const long long n_rows = (long long)B * C * R;
         const long long total = n_rows * cab;
-        const int gsz = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+        const long long work = (k / cab >= 32) ? total * 32 : total;            // a warp per long window
+        const int gsz = (int)std::min<long long>((work + 255) / 256, (long long)sm_count() * 16);
         SPK_CUDA(launch_k(sp_cabins_generic_kernel, dim3(gsz), dim3(256), 0, (cudaStream_t)stream, (const float*)sp_cube, k, cab, n_rows, cabins, cab_arg));
     }
     return SPK_OK;
@@ -936,7 +962,8 @@ extern "C" int sp_cabins_fwd_f32(const float* windows, long long rows, int k, in
     if (rows == 0) return SPK_OK;
     if (!windows || !cabins || !cab_arg) return fail(SPK_E_BADARG, "sp_cabins_fwd_f32: null pointer");
     const long long total = rows * cab;
-    const int g = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+    const long long work = (k / cab >= 32) ? total * 32 : total;                // a warp per long window
+    const int g = (int)std::min<long long>((work + 255) / 256, (long long)sm_count() * 16);
     SPK_CUDA(launch_k(sp_cabins_generic_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, windows, k, cab, rows, cabins, cab_arg));
     return SPK_OK;
 }

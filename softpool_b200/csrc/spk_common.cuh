@@ -35,7 +35,7 @@ int max_optin_smem();    // cudaDevAttrMaxSharedMemoryPerBlockOptin of the curre
 size_t chamfer_dense_workspace_bytes(int B, int n, int m);
 int chamfer_dense_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
                           float* dist2, int32_t* idx1, int32_t* idx2, float* loss /* or NULL */, void* ws,
-                          size_t ws_bytes, cudaStream_t st);
+                          size_t ws_bytes, cudaStream_t st, int B2 /* distinct xyz2 samples: B for the plain call */);
 // tensor-core Chamfer forward, sorted search (chamfer_tc.cu): clouds sorted along a Hilbert curve, chunk filter on the tensor pipe
 bool chamfer_tc_supported(int n, int m);      // cloud sizes the sorted tensor path handles
 size_t chamfer_tc_workspace_bytes(int B, int n, int m);

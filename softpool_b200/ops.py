@@ -200,13 +200,75 @@ def chamfer_mean_loss(xyz1, xyz2):
     return _ChamferMeanLoss.apply(xyz1, xyz2)
 
 
+class _ChamferMultiMeanLoss(torch.autograd.Function):
+    """preds (P, B, n, 3) stacked predictions, gt (B, m, 3) -> loss (P, B): mean(dist1,1) + mean(dist2,1) of every
+    prediction against the SAME ground truth -- the training step's `self.CD(output1[i], gt)` calls (train.py:68-86) as one
+    forward call (chamfer_fwd_multi_f32: one prep + one tensor launch, the ground truth formatted once per sample) and one
+    backward call; the ground truth's gradient is the sum over the predictions."""
+
+    @staticmethod
+    def forward(ctx, preds, gt):
+        require_cuda(preds, "preds", torch.float32)
+        require_cuda(gt, "gt", torch.float32)
+        if preds.dim() != 4 or preds.shape[3] != 3 or gt.dim() != 3 or gt.shape[2] != 3 or preds.shape[1] != gt.shape[0]:
+            raise RuntimeError("chamfer_multi: preds must be (P,B,n,3) and gt (B,m,3)")
+        preds, gt = preds.contiguous(), gt.contiguous()
+        P, B, n, _ = preds.shape
+        m = gt.shape[1]
+        dev = preds.device
+        dist1 = torch.empty((P * B, n), dtype=torch.float32, device=dev)
+        dist2 = torch.empty((P * B, m), dtype=torch.float32, device=dev)
+        idx1 = torch.empty((P * B, n), dtype=torch.int32, device=dev)
+        idx2 = torch.empty((P * B, m), dtype=torch.int32, device=dev)
+        loss = torch.empty((P * B,), dtype=torch.float32, device=dev)
+        L = _lib.lib()
+        ws_bytes = int(L.chamfer_fwd_workspace_bytes(P * B, n, m))
+        ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(L.chamfer_fwd_multi_f32(ptr(preds), ptr(gt), P, B, n, m, ptr(dist1), ptr(dist2), ptr(idx1), ptr(idx2),
+                                          ptr(loss), ptr(ws), ws_bytes, stream_of(preds)), "chamfer_fwd_multi_f32")
+        ctx.save_for_backward(preds, gt, idx1, idx2)
+        ctx.mark_non_differentiable(idx1, idx2)
+        return loss.view(P, B), dist1.view(P, B, n), dist2.view(P, B, m), idx1.view(P, B, n), idx2.view(P, B, m)
+
+    @staticmethod
+    def backward(ctx, g_loss, g_d1, g_d2, _i1, _i2):
+        preds, gt, idx1, idx2 = ctx.saved_tensors
+        P, B, n, _ = preds.shape
+        m = gt.shape[1]
+        g1 = torch.zeros((P * B, n), dtype=torch.float32, device=preds.device)
+        g2 = torch.zeros((P * B, m), dtype=torch.float32, device=preds.device)
+        if g_loss is not None:
+            g = g_loss.contiguous().to(torch.float32).view(P * B)
+            g1 = g1 + (g / n)[:, None]
+            g2 = g2 + (g / m)[:, None]
+        if g_d1 is not None:
+            g1 = g1 + g_d1.reshape(P * B, n)
+        if g_d2 is not None:
+            g2 = g2 + g_d2.reshape(P * B, m)
+        gt_rep = gt.unsqueeze(0).expand(P, B, m, 3).reshape(P * B, m, 3)           # (the backward kernel pairs rows one to one)
+        grad1, grad2 = chamfer_backward(preds.view(P * B, n, 3), gt_rep, g1, g2, idx1, idx2)
+        return grad1.view(P, B, n, 3), grad2.view(P, B, m, 3).sum(0)
+
+
+def chamfer_multi(preds, gt):
+    """Several predictions against one ground truth in one call.  preds: (P,B,n,3) tensor or a list of P (B,n,3) tensors of the
+    same n; gt (B,m,3).  -> loss (P,B), dist1 (P,B,n), dist2 (P,B,m), idx1 (P,B,n) i32, idx2 (P,B,m) i32; differentiable in
+    preds and gt through loss / dist1 / dist2.  Bit-identical to P separate chamferDist calls."""
+    if isinstance(preds, (list, tuple)):
+        preds = torch.stack(list(preds), 0)
+    return _ChamferMultiMeanLoss.apply(preds, gt)
+
+
 def chamfer_backward(xyz1, xyz2, g1, g2, idx1, idx2):
     """-> grad_xyz1 (B,n,3), grad_xyz2 (B,m,3) (chamfer.cu:155-196)."""
+    xyz1, xyz2 = _chamfer_inputs(xyz1, xyz2)       # (contiguous: an expanded / strided view must not reach the kernel as it is)
     B, n, _ = xyz1.shape
     m = xyz2.shape[1]
     dev = xyz1.device
     g1 = g1.contiguous()          # dist_chamfer.py:37-38 does the same
     g2 = g2.contiguous()
+    idx1, idx2 = idx1.contiguous(), idx2.contiguous()
     grad1 = torch.empty((B, n, 3), dtype=torch.float32, device=dev)
     grad2 = torch.empty((B, m, 3), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):

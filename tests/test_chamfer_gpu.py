@@ -272,6 +272,36 @@ def test_non_finite_inputs_match_the_reference_order(B, n, m):
     assert np.isnan(r[0][0]).any()          # the case really exercises NaN results
 
 
+@pytest.mark.parametrize("P,B,n,m", [(3, 4, 2048, 2048), (2, 3, 700, 1100), (4, 2, 100, 90), (3, 1, 4096, 5000)])
+def test_multi_prediction_call_matches_separate_calls(P, B, n, m):
+    """chamfer_fwd_multi_f32 / ops.chamfer_multi: P predictions against one shared ground truth (train.py:68-86) in one call
+    -- bit-identical to P separate calls (which are bit-identical to the oracle), loss within float rounding, gradients of
+    the predictions as in the separate calls and the ground truth's gradient = their sum."""
+    from softpool_b200 import ops
+    rng = np.random.default_rng(P * 100 + n)
+    preds = (rng.random((P, B, n, 3), dtype=np.float32) - 0.5)
+    gt = (rng.random((B, m, 3), dtype=np.float32) - 0.5)
+    preds[1, 0, :5] = gt[0, :5]                               # zero distances / ties
+    tp = torch.from_numpy(preds).to(dev()).requires_grad_(True)
+    tg = torch.from_numpy(gt).to(dev()).requires_grad_(True)
+    loss, d1, d2, i1, i2 = ops.chamfer_multi(tp, tg)
+    w = torch.from_numpy(rng.random((P, B), dtype=np.float32)).to(dev())
+    (loss * w).sum().backward()
+    g_gt = torch.zeros_like(tg)
+    for p in range(P):
+        r = co.forward(preds[p], gt)
+        assert np.array_equal(i1[p].cpu().numpy(), r[2]) and np.array_equal(i2[p].cpu().numpy(), r[3])
+        assert np.array_equal(d1[p].detach().cpu().numpy().view(np.uint32), r[0].view(np.uint32))
+        assert np.array_equal(d2[p].detach().cpu().numpy().view(np.uint32), r[1].view(np.uint32))
+        np.testing.assert_allclose(loss[p].detach().cpu().numpy(), r[0].mean(1) + r[1].mean(1), rtol=1e-5, atol=1e-9)
+        a = torch.from_numpy(preds[p]).to(dev()).requires_grad_(True)
+        g = torch.from_numpy(gt).to(dev()).requires_grad_(True)
+        (ops.chamfer_mean_loss(a, g) * w[p]).sum().backward()
+        torch.testing.assert_close(tp.grad[p], a.grad, rtol=1e-4, atol=1e-7)
+        g_gt += g.grad
+    torch.testing.assert_close(tg.grad, g_gt, rtol=1e-4, atol=1e-7)
+
+
 def test_random_shapes_vs_oracle():
     """40 random cloud sizes on both sides of the tensor-path threshold, ragged against the 128/1024 tiling."""
     rng = np.random.default_rng(77)

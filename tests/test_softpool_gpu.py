@@ -181,10 +181,15 @@ def test_softpoolfeat_surface():
     assert chosen.shape == (2, 3, 2048)
 
 
-def test_train2cabins_standalone():
+@pytest.mark.parametrize("k", [50, 2100])
+def test_train2cabins_standalone(k):
+    """k = 50: short windows (a thread per window); k = 2100: windows of 262 slots (a warp per window), trailing slots ignored;
+    ties, NaN and +-0 inside the windows follow torch.max (first maximum, NaN wins)."""
     import softpool_b200 as spb
     rng = np.random.default_rng(3)
-    w = np.round(rng.standard_normal((2, 3, 4, 50), dtype=np.float32) * 4) / 4
+    w = np.round(rng.standard_normal((2, 3, 4, k), dtype=np.float32) * 4) / 4
+    w[0, 0, 0, 5] = np.nan; w[0, 0, 0, k // 2] = np.nan           # NaN wins, the first one
+    w[0, 1, 1, :] = -0.0; w[0, 1, 1, 7::11] = 0.0                 # -0 == +0: the first slot wins
     wt = torch.from_numpy(w).to(dev()).requires_grad_(True)
     cab = spb.train2cabins(wt, 8)
     ref, ref_arg = so.window_argmax(w, 8)
@@ -192,7 +197,7 @@ def test_train2cabins_standalone():
     g = rng.standard_normal(ref.shape, dtype=np.float32)
     cab.backward(torch.from_numpy(g).to(dev()))
     expect = np.zeros_like(w)
-    wl = 50 // 8
+    wl = k // 8
     np.put_along_axis(expect, ref_arg.astype(np.int64) + 0, g, axis=-1)
     assert ref_arg.max() < 8 * wl
     assert np.array_equal(wt.grad.cpu().numpy(), expect)
