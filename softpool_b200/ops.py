@@ -97,6 +97,44 @@ def softpool_gather(x, idx, cab):
     return _SoftPoolGather.apply(x, idx, int(cab))
 
 
+class _SelectPoints(torch.autograd.Function):
+    """Index-driven glue: any per-point tensor t (B,F,N) picked by the SoftPool index list idx (B,R,k) ->
+    (B,F,R*k), with the same gather kernel (no window max) instead of the reference's
+    `one_hot -> cat -> unsqueeze(2).repeat(1,1,R,1) -> torch.gather(index=sp_idx.long())` (softpool.py:218-231) and
+    `torch.gather(part, dim=2, index=sp_idx[:, :3, 0, :].long())` (model.py:283-285).  Backward = the gather backward."""
+
+    @staticmethod
+    def forward(ctx, t, idx):
+        require_cuda(t, "t", torch.float32)
+        require_cuda(idx, "idx", torch.int32)
+        t, idx = t.contiguous(), idx.contiguous()
+        B, Fd, N = t.shape
+        _, R, k = idx.shape
+        out = torch.empty((B, Fd, R, k), dtype=torch.float32, device=t.device)
+        with torch.cuda.device(t.device):
+            check(_lib.lib().sp_gather_fwd_f32(ptr(t), ptr(idx), B, Fd, N, R, k, 1, ptr(out), None, None, stream_of(t)),
+                  "sp_gather_fwd_f32")
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, Fd, N, R, k)
+        return out.view(B, Fd, R * k)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        B, Fd, N, R, k = ctx.dims
+        g = g.contiguous().view(B, Fd, R, k)
+        grad = torch.empty((B, Fd, N), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(_lib.lib().sp_gather_bwd_f32(ptr(g), None, ptr(idx), None, B, Fd, N, R, k, 1, ptr(grad), stream_of(g)),
+                  "sp_gather_bwd_f32")
+        return grad, None
+
+
+def softpool_select_points(t, idx):
+    """t (B,F,N) f32, idx (B,R,k) i32 -> (B,F,R*k): t[b,f,idx[b,r,j]] at column r*k+j (see _SelectPoints)."""
+    return _SelectPoints.apply(t, idx)
+
+
 class _Cabins(torch.autograd.Function):
     """Standalone train2cabins (softpool.py:71-85) with its MaxBackward."""
 

@@ -87,6 +87,7 @@ class SoftPool(nn.Module):
         val_activa = self.sorter.conv1d(x)                    # library 1x1 conv; boundary of the native path
         idx, sp_idx, id_activa = ops.softpool_topk(val_activa.detach(), self.pnt_per_sort)
         sp_cube, cabins = ops.softpool_gather(x, idx, self.num_cabin)
+        self.last_idx = idx                                   # (B,R,k) i32: the integer index list behind the float sp_idx cube
         return sp_cube, sp_idx, cabins, id_activa
 
 
@@ -111,11 +112,30 @@ class SoftPoolFeat(nn.Module):
         x = F.relu(self.bn2(self.conv2(x)))
         return self.bn3(self.conv3(x))
 
+    def select_points(self, t):
+        """t (B,F,N) gathered by the index list of the last forward -> (B,F,R*k): the caller's
+        `torch.gather(part, dim=2, index=sp_idx[:, :3, 0, :].long())` (model.py:283-285) and the reference's own
+        `point_wi_seg` gather (softpool.py:218-231) without the one_hot / cat / repeat / float-index detour."""
+        return ops.softpool_select_points(t, self.softpool.last_idx)
+
+    def point_wi_seg(self, x, x_seg=None):
+        """The reference's `point_wi_seg` tensor (softpool.py:218-231): region one-hot of every point (or the given
+        segmentation) stacked on xyz, (B, R+3, N), picked by the index list -> (B, R+3, 1, R*k).  Dead in the reference
+        (it only feeds the commented-out `feature` return) but part of its forward; emitted index-driven here."""
+        idx = self.softpool.last_idx
+        B, R, k = idx.shape
+        if x_seg is None:
+            seg = F.one_hot(self.softpool.last_id_activa.to(torch.int64), self.regions).transpose(1, 2).float()
+        else:
+            seg = x_seg.float()
+        return ops.softpool_select_points(torch.cat((seg, x), 1).contiguous(), idx).view(B, seg.shape[1] + x.shape[1], 1, R * k)
+
     def forward(self, x, x_seg=None):
         part = x
         sp_cube, sp_idx, cabins, id_activa = self.softpool(self.mlp(x))
+        self.softpool.last_id_activa = id_activa
         # region one-hot (or the given segmentation) stacked on xyz, gathered by the same indices
-        # (reference softpool.py:218-231); the result only feeds the commented-out `feature` return
+        # (reference softpool.py:218-231); the result only feeds the commented-out `feature` return: see point_wi_seg()
         B = sp_cube.shape[0]
         flat = self.regions * self.sp_points
         sp_cube = sp_cube.view(B, sp_cube.shape[1], 1, flat)

@@ -280,6 +280,31 @@ def test_tie_order_is_cuda_torch_sort():
             assert torch.equal(idx.long(), ref), "B=%d R=%d N=%d k=%d stable=%s" % (B, R, N, k, stable)
 
 
+def test_index_driven_glue_matches_the_reference_gathers():
+    """SURVEY 8(f-1), second half: `input_chosen` (model.py:283-285) and `point_wi_seg` (softpool.py:218-231) emitted by the
+    gather kernel from the integer index list, against the reference's own one_hot / cat / repeat / torch.gather composition
+    on the float index cube -- exact copies, and the gradient of the selection."""
+    import softpool_b200 as spb
+    torch.manual_seed(2)
+    R, ratio, N = 8, 8, 1024
+    m = spb.SoftPoolFeat(num_points=N, regions=R, sp_points=N, sp_ratio=ratio).to(dev())
+    part = (torch.rand(3, 3, N) - 0.5).to(dev()).requires_grad_(True)
+    sp_cube, cabins, sp_idx = m(part)
+    chosen = m.select_points(part)                                                        # (B,3,R*k)
+    ref = torch.gather(part, dim=2, index=sp_idx[:, :3, 0, :].long())                     # model.py:283-285
+    assert torch.equal(chosen, ref)
+    g = torch.randn_like(chosen)
+    (ga,) = torch.autograd.grad(chosen, part, g, retain_graph=True)
+    (gb,) = torch.autograd.grad(ref, part, g, retain_graph=True)
+    torch.testing.assert_close(ga, gb, rtol=1e-5, atol=1e-6)
+    # the reference's point_wi_seg, statement for statement (softpool.py:218-231)
+    id_activa = m.softpool.last_id_activa
+    one_hot = torch.nn.functional.one_hot(id_activa.to(torch.int64), R).transpose(1, 2)
+    pws = torch.cat((one_hot.float(), part.detach()), 1).unsqueeze(2).repeat(1, 1, R, 1)
+    pws = torch.gather(pws, dim=3, index=sp_idx.view(3, R + 3, R, N // ratio).long())
+    assert torch.equal(m.point_wi_seg(part.detach()).view(3, R + 3, R, N // ratio), pws)
+
+
 def test_softpoolfeat_matches_reference_golden():
     """Reference SoftPoolFeat (softpool.py:174-241, train-mode BatchNorm) on tests/golden/softpool_feat.npz: the fixture's
     live weights are loaded into the drop-in module.  cuDNN/cuBLAS convolutions on the GPU round differently from the CPU
@@ -297,10 +322,18 @@ def test_softpoolfeat_matches_reference_golden():
     assert not unexpected and all(key.startswith("softpool.conv2d_") or "running_" in key or "num_batches" in key for key in missing)
     m.train()
     x = torch.from_numpy(g["x"]).to(dev())
-    with torch.no_grad():
-        feat = m.mlp(x)
-        keys = m.softpool.sorter.conv1d(feat)
-        sp_cube, cabins, sp_idx = m(x)
+    # the fixture was made on the CPU in fp32; cuDNN may otherwise pick TF32 convolutions (allowed by default), whose
+    # 1e-3 errors are the library conv's business, not the path under test (tools/f1_conv_key_study.py measures them)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            feat = m.mlp(x)
+            keys = m.softpool.sorter.conv1d(feat)
+            sp_cube, cabins, sp_idx = m(x)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     np.testing.assert_allclose(feat.cpu().numpy(), g["feat"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(keys.cpu().numpy(), g["keys"], rtol=1e-4, atol=1e-5)
     assert sp_cube.shape == g["sp_cube"].shape and cabins.shape == g["cabins"].shape and sp_idx.shape == g["sp_idx"].shape
