@@ -769,8 +769,18 @@ chamfer_search_kernel(const SearchParams p) {
                 t = fmaf(t, 1.00390625f, mt.tau);
                 uint32_t t16 = (uint32_t)__half_as_ushort(__float2half_ru(t));
                 if (!(t == t) || t16 > 0x7C00u) t16 = 0x7C00u;       // NaN / garbage: everything passes
-                uint32_t m[4];
-                build_mask(w, t16, m);
+                uint32_t m[4] = {0u, 0u, 0u, 0u};
+                bool any = true;
+                if (passes > 1) {
+                    // most passes of a large cloud hold no candidate at all for a query (its neighbours sit in one or two of
+                    // them): the row minimum (22 packed min instructions) decides before the mask is built (192)
+                    uint32_t rm = __vimin3_u16x2(w[0], w[1], w[2]);
+#pragma unroll
+                    for (int i = 3; i + 1 < 64; i += 2) rm = __vimin3_u16x2(rm, w[i], w[i + 1]);
+                    rm = __vminu2(rm, w[63]);
+                    any = min(rm & 0xFFFFu, rm >> 16) <= t16;
+                }
+                if (any) build_mask(w, t16, m);
                 TC_COUNT(0, 1); TC_COUNT(2, __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]));
                 // ---- box test (float32, this query's best so far); survivors go to the queue -------------------------------
 #pragma unroll

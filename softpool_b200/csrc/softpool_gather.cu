@@ -784,6 +784,7 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
     // rows so long that only ONE CTA fits an SM (two row buffers + index list > half the shared memory, e.g. N = 16384):
     // a 1024-thread CTA keeps the SM busy (no measurable difference at N = 16384 once the window max ran a warp per window; kept for the long-row case)
     if (fixed + 2 * (size_t)T * row_bytes > (size_t)110 * 1024) threads = 1024;
+    else if (fixed + 2 * (size_t)T * row_bytes > (size_t)72 * 1024 && !tune_env("SPK_FWD_THREADS")) threads = 512;   // two CTAs per SM: 32 warps
     // the per-group hoisting only pays when a tile holds several rows (measured: N=2048 33 vs 34.5 us; one row per tile, N=8192: 169 vs 145 us)
     p.q_cols = T >= 2 && p.vec4 && ((RK >> 2) % threads) == 0 && (!want_cab || p.cab_fast) && !tune_env("SPK_FWD_NO_QCOLS");
     const size_t smem = fixed + 2 * (size_t)T * row_bytes;
@@ -795,7 +796,8 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
         SPK_CUDA(launch_k(kern, dim3((int)grid), dim3(nt), smem, (cudaStream_t)stream, p));
         return SPK_OK;
     };
-    const int rc = threads == 128 ? launch(sp_gather_fwd_kernel<128>, 128) : threads == 1024 ? launch(sp_gather_fwd_kernel<1024>, 1024) : launch(sp_gather_fwd_kernel<256>, 256);
+    const int rc = threads == 128 ? launch(sp_gather_fwd_kernel<128>, 128) : threads == 1024 ? launch(sp_gather_fwd_kernel<1024>, 1024) :
+                   threads == 512 ? launch(sp_gather_fwd_kernel<512>, 512) : launch(sp_gather_fwd_kernel<256>, 256);
     if (rc != SPK_OK) return rc;
     if (want_cab && !p.cab_fast) {
         const long long n_rows = (long long)B * C * R;
