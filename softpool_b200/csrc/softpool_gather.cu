@@ -149,7 +149,14 @@ sp_gather_fwd_kernel(const GatherFwdParams p) {
                         if (!(v.z <= best) && best == best) { best = v.z; off = 2; }
                         if (!(v.w <= best) && best == best) { best = v.w; off = 3; }
                         uint32_t woff = off + lane_off;
-                        if (G > 1) {
+                        if (G >= 16) {
+                            // two warp reductions (REDUX) on the window's own lanes: the greatest key, then the lowest offset holding it
+                            // (measured: G = 16, N = 4096: 62 -> 51 us; G = 8, k = 256: 32.5 -> 35 us, so the butterflies stay there)
+                            const uint32_t gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
+                            const uint32_t key = order_key(best);
+                            const uint32_t kmax = __reduce_max_sync(gmask, key);
+                            woff = __reduce_min_sync(gmask, key == kmax ? woff : 0xFFFFu);
+                        } else if (G > 1) {
                             // two 32-bit butterflies: the window's greatest key, then the lowest offset that holds it
                             const uint32_t key = order_key(best);
                             uint32_t kmax = key;
@@ -187,7 +194,16 @@ sp_gather_fwd_kernel(const GatherFwdParams p) {
                     if (!(v.z <= best) && best == best) { best = v.z; off = 2; }
                     if (!(v.w <= best) && best == best) { best = v.w; off = 3; }
                     uint32_t woff = off + ((uint32_t)(q & (G - 1)) << 2);         // offset inside the window
-                    if (G > 1) {
+                    if (G >= 16) {
+                        // 16..32 lanes per window (a whole warp at N = 8192, k = 1024): two warp reductions (REDUX) -- the greatest key, then
+                        // the lowest offset holding it -- instead of five 64-bit shuffle steps (the forward was issue-bound there:
+                        // 109 M warp instructions, issue 73 %)
+                        // (G = 16: the same on the window's own lanes -- disjoint member masks inside a warp)
+                        const uint32_t gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
+                        const uint32_t key = order_key(best);
+                        const uint32_t kmax = __reduce_max_sync(gmask, key);
+                        woff = __reduce_min_sync(gmask, key == kmax ? woff : 0xFFFFFFFFu);
+                    } else if (G > 1) {
                         // ... then one packed word per lane: greater key wins, equal keys -> lower offset
                         uint64_t pk = ((uint64_t)order_key(best) << 32) | (uint32_t)(0xFFFFFFFFu - woff);
                         for (int d = 1; d < G; d <<= 1) {

@@ -170,6 +170,19 @@ def cabins_max(windows, cab):
     return _Cabins.apply(windows, int(cab))
 
 
+def gather_operation(features, idx):
+    """Drop-in for the MSN decoder's `gather_operation` (reference MSN/MDS/MDS_module.py:40-84, kernels
+    MSN/MDS/MDS_cuda.cu:29-75): features (B,C,N) f32, idx (B,npoint) int32 -> (B,C,npoint) = features[b,c,idx[b,j]].
+    Forward and backward run on the SoftPool gather kernels (one region of npoint slots).  The backward sums
+    deterministically; the reference's `grad_points[..] += grad_out[..]` (MDS_cuda.cu:66-67, its atomicAdd commented out)
+    races when an index repeats.  The indices of one sample must be DISTINCT, which is what its producer, minimum density
+    sampling, returns (the inverse table of the backward holds one slot per point and region)."""
+    require_cuda(idx, "idx", torch.int32)
+    if idx.dim() != 2:
+        raise RuntimeError("gather_operation: idx must be (B, npoint)")
+    return softpool_select_points(features, idx.unsqueeze(1))
+
+
 # ------------------------------------------------------------------------------------------
 # Chamfer
 # ------------------------------------------------------------------------------------------

@@ -305,6 +305,23 @@ def test_index_driven_glue_matches_the_reference_gathers():
     assert torch.equal(m.point_wi_seg(part.detach()).view(3, R + 3, R, N // ratio), pws)
 
 
+def test_gather_operation_matches_the_msn_op():
+    """MSN `gather_operation` (MDS_module.py:40-84; model.py:317-337 feeds it the distinct indices of minimum density
+    sampling): forward = features[b, c, idx[b, j]], backward = the scatter of the upstream gradient (summed, no race)."""
+    from softpool_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    for (B, C, N, m) in [(4, 3, 8192, 2048), (2, 256, 2048, 512), (3, 7, 1001, 333)]:
+        feat = torch.randn(B, C, N, generator=g).to(dev()).requires_grad_(True)
+        idx = torch.stack([torch.randperm(N, generator=g)[:m] for _ in range(B)]).to(torch.int32).to(dev())
+        out = ops.gather_operation(feat, idx)
+        ref = torch.gather(feat, 2, idx.long()[:, None].expand(B, C, m))
+        assert out.shape == (B, C, m) and torch.equal(out, ref)
+        up = torch.randn(B, C, m, generator=g).to(dev())
+        (ga,) = torch.autograd.grad(out, feat, up, retain_graph=True)
+        (gb,) = torch.autograd.grad(ref, feat, up)
+        assert torch.equal(ga, gb)                              # distinct indices: every element has one contribution
+
+
 def test_softpoolfeat_matches_reference_golden():
     """Reference SoftPoolFeat (softpool.py:174-241, train-mode BatchNorm) on tests/golden/softpool_feat.npz: the fixture's
     live weights are loaded into the drop-in module.  cuDNN/cuBLAS convolutions on the GPU round differently from the CPU
