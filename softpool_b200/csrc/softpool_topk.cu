@@ -18,6 +18,7 @@
 namespace spk {
 
 constexpr int TOPK_THREADS = 256;
+__device__ __forceinline__ int next_pow2_dev(int v) { return v <= 1 ? 1 : 1 << (32 - __clz(v - 1)); }
 
 __device__ __forceinline__ void ce_stage(uint64_t* buf, int len, int size, int stride, int tid,
                                          int nthr) {
@@ -60,12 +61,12 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot /*[8]*/
 }
 
 __global__ void __launch_bounds__(TOPK_THREADS)
-sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K2, int vec_ok,
+sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K2, int KS, int vec_ok,
                int32_t* __restrict__ idx, float* __restrict__ sp_idx,
                int64_t* __restrict__ id_activa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);                 // K2 survivors
-    uint32_t* sk = reinterpret_cast<uint32_t*>(sel + K2);                  // E*256 keys, [e][t]
+    uint32_t* sk = reinterpret_cast<uint32_t*>(sel + KS);                  // E*256 keys, [e][t]
     int* hist = reinterpret_cast<int*>(sk + (size_t)E * TOPK_THREADS);     // 3 x 8 warps x 16 bins
     __shared__ int warp_tot[TOPK_THREADS / 32];
     __shared__ uint32_t cand_list[32];
@@ -132,7 +133,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
                 if (e0 + u < E) sk[(e0 + u) * TOPK_THREADS + tid] = (n0 + e0 + u < N) ? order_key(v[u]) : 0u;
         }
     }
-    for (int i = tid; i < K2; i += TOPK_THREADS) sel[i] = 0ull;
+    for (int i = tid; i < KS; i += TOPK_THREADS) sel[i] = 0ull;
     for (int i = tid; i < 3 * 8 * 16; i += TOPK_THREADS) hist[i] = 0;
     if (tid == 0) cand_cnt = 0;
 
@@ -170,6 +171,44 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     __syncthreads();
     TQ(1);
 
+    // ---- 2a. small k (k <= 32, the BASELINE configuration): no radix rounds at all.  The J = ceil(k / 8) largest of a warp's
+    // 32 thread-maxima are J distinct keys, so T0 = the smallest of the 8 warps' J-th largest has at least 8 J >= k keys at or
+    // above it: the k-th largest key is >= T0.  Everything >= T0 (about 2 k keys; all ties of the k-th key included) is
+    // compacted in index order and sorted; the first k words are the stable descending prefix.  Falls through to the radix
+    // select when more than KS keys survive (heavy ties).
+    int K2s = K2;                                        // slots the survivor sort works on
+    bool done_fast = false;
+    if (k <= 32 && KS >= 256) {
+        __shared__ uint32_t warp_thr[TOPK_THREADS / 32];
+        uint32_t tmax = 0;
+        for (int e = 0; e < E; ++e) tmax = max(tmax, sk[e * TOPK_THREADS + tid]);
+        const int J = (k + 7) >> 3;
+        const int lane_ = tid & 31;
+        uint32_t v = tmax, jth = 0;
+        for (int j = 0; j < J; ++j) {
+            jth = __reduce_max_sync(0xFFFFFFFFu, v);
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, v == jth);
+            if (lane_ == __ffs((int)bal) - 1) v = 0u;            // remove ONE holder of the maximum
+        }
+        if (lane_ == 0) warp_thr[tid >> 5] = jth;
+        __syncthreads();
+        uint32_t T0 = warp_thr[0];
+#pragma unroll
+        for (int w = 1; w < TOPK_THREADS / 32; ++w) T0 = min(T0, warp_thr[w]);
+        int mine = 0;
+        for (int e = 0; e < E; ++e) mine += sk[e * TOPK_THREADS + tid] >= T0;
+        int total;
+        int pos = block_exclusive_scan(mine, warp_tot, tid, total);
+        if (total <= KS && T0 > 0u) {                            // (T0 == 0: padding keys could be counted -> generic path)
+            for (int e = 0; e < E; ++e) {
+                const uint32_t key = sk[e * TOPK_THREADS + tid];
+                if (key >= T0) sel[pos++] = ((uint64_t)key << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)(n0 + e));
+            }
+            K2s = max(2, next_pow2_dev(total));
+            done_fast = true;
+        }
+    }
+
     // ---- 2. radix select of the k-th largest key, 4 bits per round ---------------------------------------
     // Warp-private 16-bin histograms of the keys that still match the decided prefix (shared-memory
     // atomics), one barrier per round; every warp then reduces the 8 histograms itself.
@@ -178,7 +217,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     int fin_sh = -1;                                     // >= 0: the select stopped early with bits [31:fin_sh] decided
     int want = k;                                        // rank still to be located inside the prefix bucket
     const int lane = tid & 31, warp = tid >> 5;
-    for (int round = 0; round < 8; ++round) {
+    for (int round = 0; round < 8 && !done_fast; ++round) {
         const int sh = 28 - 4 * round;
         int* H = hist + (round % 3) * (8 * 16);
         const uint32_t pre = (round == 0) ? 0u : (V >> (sh + 4));
@@ -215,7 +254,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         if (tid < 8 * 16) Hz[tid] = 0;
     }
 
-    if (fin_sh >= 0) {
+    if (fin_sh >= 0 && !done_fast) {
         // the bucket's <= 32 keys -> shared list; warp 0 finds the one with exactly want-1 keys ahead of it
         const uint32_t pre = V >> fin_sh;
 #pragma unroll 4
@@ -241,6 +280,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
 
     TQ(2);
     // ---- 3. compaction in index order ---------------------------------------------------------------------
+    if (!done_fast) {
     int my_gt = 0, my_eq = 0;
 #pragma unroll 4
     for (int e = 0; e < E; ++e) {
@@ -261,29 +301,30 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         if (key == V) { take = eq_rank < need; ++eq_rank; }
         if (take) { sel[pos++] = ((uint64_t)key << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)(n0 + e)); }
     }
+    }
 
     TQ(3);
     // ---- 4. sort the survivors (descending; unique words => stable order) ---------------------------------
-    if (K2 <= 32) {
+    if (K2s <= 32) {
         // one warp, one word per lane, bitonic network on shuffles: no barriers
         __syncthreads();
         if (warp == 0) {
-            uint64_t v = (lane < K2) ? sel[lane] : 0ull;
-            for (int size = 2; size <= K2; size <<= 1)
+            uint64_t v = (lane < K2s) ? sel[lane] : 0ull;
+            for (int size = 2; size <= K2s; size <<= 1)
                 for (int stride = size >> 1; stride > 0; stride >>= 1) {
                     const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, v, stride);
-                    const bool desc = (lane & size) == 0 || size == K2;
+                    const bool desc = (lane & size) == 0 || size == K2s;
                     const bool lower = (lane & stride) == 0;          // this lane keeps the first of the pair
                     v = (lower == desc) ? (o > v ? o : v) : (o < v ? o : v);
                 }
-            if (lane < K2) sel[lane] = v;
+            if (lane < K2s) sel[lane] = v;
         }
     } else {
         int prev = 64;
-        for (int size = 2; size <= K2; size <<= 1)
+        for (int size = 2; size <= K2s; size <<= 1)
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
                 stage_sync(stride, prev);
-                ce_stage(sel, K2, size, stride, tid, TOPK_THREADS);
+                ce_stage(sel, K2s, size, stride, tid, TOPK_THREADS);
                 prev = stride;
             }
     }
@@ -342,10 +383,11 @@ extern "C" int sp_topk_f32(const float* keys, int B, int R, int N, int k, int32_
     const int K2 = max(2, next_pow2(k));
     int E = (N + TOPK_THREADS - 1) / TOPK_THREADS;
     if (E > 4) E = (E + 3) & ~3;                       // float4 path wants E % 4 == 0
-    const size_t smem = (size_t)K2 * sizeof(uint64_t) + (size_t)E * TOPK_THREADS * sizeof(uint32_t) + 3 * 8 * 16 * sizeof(int);
+    const int KS = k <= 32 ? std::max(K2, 256) : K2;       // small k: room for every key at or above the shortcut's threshold
+    const size_t smem = (size_t)KS * sizeof(uint64_t) + (size_t)E * TOPK_THREADS * sizeof(uint32_t) + 3 * 8 * 16 * sizeof(int);
     if (smem > 48 * 1024)
         SPK_CUDA(cudaFuncSetAttribute(sp_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SPK_CUDA(launch_k(sp_topk_kernel, dim3(B * R), dim3(TOPK_THREADS), smem, (cudaStream_t)stream, keys, R, N, k, E, K2, vec_ok, idx, sp_idx, id_activa));
+    SPK_CUDA(launch_k(sp_topk_kernel, dim3(B * R), dim3(TOPK_THREADS), smem, (cudaStream_t)stream, keys, R, N, k, E, K2, KS, vec_ok, idx, sp_idx, id_activa));
     return SPK_OK;
 }
 

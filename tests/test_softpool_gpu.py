@@ -263,6 +263,23 @@ def test_full_size_vs_oracle(k):
     assert np.array_equal(bits(out["grad_x"]), bits(ref_g))
 
 
+@pytest.mark.parametrize("N", [256, 300, 1000, 2048, 4096, 16384])
+def test_small_k_shortcut_vs_oracle(N):
+    """k <= 32 takes the threshold shortcut of sp_topk_kernel (no radix rounds): random keys, heavy ties (falls back to the
+    radix select when too many keys tie at the threshold), NaN / inf, rows with fewer than k distinct values."""
+    rng = np.random.default_rng(N)
+    from softpool_b200 import ops
+    for k in (1, 7, 32):
+        keys = rng.standard_normal((3, 5, N), dtype=np.float32)
+        keys[0, 1] = np.round(keys[0, 1] * 2) / 2                       # heavy ties
+        keys[0, 2] = 0.5                                                # all equal
+        keys[1, 0, ::3] = np.inf; keys[1, 1, 5] = np.nan; keys[1, 1, N - 1] = np.nan
+        keys[2, 3, : N // 2] = -np.inf
+        idx, sp_idx, id_activa = ops.softpool_topk(torch.from_numpy(keys).to(dev()), k)
+        ref = so.topk_indices(keys, k)
+        assert np.array_equal(idx.cpu().numpy(), ref), "N=%d k=%d" % (N, k)
+
+
 def test_tie_order_is_cuda_torch_sort():
     """The reference's deployment path is torch.sort on CUDA tensors (softpool.py:140, default stable=False).  On tie-heavy
     keys (quantised to 1/16, all-equal rows, +-0) the library's order -- ties keep ascending point index -- must be what
