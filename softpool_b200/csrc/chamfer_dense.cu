@@ -268,7 +268,7 @@ chamfer_prep_kernel(const PrepParams p) {
     if (p.counters != nullptr && blockIdx.x == 0)
         for (int i = tid; i < p.n_counters; i += 256) p.counters[(size_t)b * p.n_counters + i] = 0;
     if (p.loss != nullptr && blockIdx.x == 0 && tid == 0) p.loss[b] = 0.f;
-    pdl_tail_trigger();
+    pdl_tail_trigger_bit<3>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -750,7 +750,7 @@ chamfer_tc_kernel(const TcParams p) {
     if (tid == 0 && blockIdx.x == 0) for (int i = 0; i < min(tlog_n, 320); ++i) printf("  t=%7lld %s %d %d\n", tlog_t[i], tlog_s[i], tlog_a[i], tlog_b[i]);
     if (tid == 0 && blockIdx.x < 2) printf("tc cta %d: chunks evaluated %d over %d (row, half, super-block) filters = %.3f each\n", blockIdx.x, S.dbg[0], S.dbg[1], (float)S.dbg[0] / (float)max(S.dbg[1], 1));
 #endif
-    pdl_tail_trigger();
+    pdl_tail_trigger_bit<2>();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

@@ -402,7 +402,7 @@ chamfer_sort_kernel(const SortParams p) {
         printf("sort kernel phases (cycles): bbox+meta %lld, cells+hist %lld, scan %lld, perm %lld, sorted rows %lld, chunk rows %lld\n",
                tph[1] - tph[0], tph[2] - tph[1], tph[3] - tph[2], tph[4] - tph[3], tph[5] - tph[4], tph[6] - tph[5]);
 #endif
-    pdl_tail_trigger();
+    pdl_tail_trigger_bit<5>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -857,7 +857,7 @@ chamfer_search_kernel(const SearchParams p) {
             p.idx[dir][(size_t)b * nq + qorig] = best_i;
         }
     }
-    pdl_tail_trigger();
+    pdl_tail_trigger_bit<6>();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {

@@ -237,7 +237,7 @@ sp_gather_fwd_kernel(const GatherFwdParams p) {
             g_pref += r;
         }
     }
-    pdl_tail_trigger();
+    pdl_tail_trigger_bit<0>();
 }
 
 // Generic window max over an already written sp_cube (any k, cab): one thread per window.
@@ -710,7 +710,7 @@ sp_gather_bwd_pull_kernel(const GatherBwdPullParams p) {
         __syncthreads();                                           // the slot and the table are free again
         g += rows;
     }
-    pdl_tail_trigger();
+    pdl_tail_trigger_bit<1>();
 }
 
 }  // namespace spk

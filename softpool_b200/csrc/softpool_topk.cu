@@ -78,9 +78,6 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     const float* krow = keys + (size_t)row * N;
     pdl_trigger();
     pdl_wait();
-#ifndef SPK_NO_TOPK_TRIGGER
-    pdl_launch_dependents();     // see spk_common.cuh: the gather's first x tiles load under this kernel
-#endif
 #ifdef SPK_TIMING
     long long tq[8]; tq[0] = clock64();
 #define TQ(i) tq[i] = clock64()
@@ -178,6 +175,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     // select when more than KS keys survive (heavy ties).
     int K2s = K2;                                        // slots the survivor sort works on
     bool done_fast = false;
+#ifndef SPK_NO_TOPK_SHORTCUT
     if (k <= 32 && KS >= 256) {
         __shared__ uint32_t warp_thr[TOPK_THREADS / 32];
         uint32_t tmax = 0;
@@ -208,6 +206,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
             done_fast = true;
         }
     }
+#endif
 
     // ---- 2. radix select of the k-th largest key, 4 bits per round ---------------------------------------
     // Warp-private 16-bin histograms of the keys that still match the decided prefix (shared-memory
@@ -304,6 +303,13 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     }
 
     TQ(3);
+#ifndef SPK_NO_TOPK_TRIGGER
+    // The gather's CTAs may start now (this kernel's own griddepcontrol.wait is long past, so everything before it in the
+    // stream is complete): their first x tiles stream in during the survivor sort + emit.  Measured on the whole step at
+    // config A: no trigger 74.1 us, trigger at kernel start 75.7 us (the waiting gather CTAs take the second-wave slots of
+    // this kernel's own CTAs), trigger here 72.2 us.
+    pdl_launch_dependents();
+#endif
     // ---- 4. sort the survivors (descending; unique words => stable order) ---------------------------------
     if (K2s <= 32) {
         // one warp, one word per lane, bitonic network on shuffles: no barriers

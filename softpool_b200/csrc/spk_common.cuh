@@ -149,9 +149,9 @@ __device__ __forceinline__ void pdl_trigger() {
 #endif
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// Unconditional trigger, used by sp_topk_kernel only and only AFTER its own pdl_wait(): everything that preceded the
-// top-k in the stream is then complete, so the next kernel (the gather) may safely read ITS OTHER inputs (x) in its
-// prologue, before its own pdl_wait() -- the x tiles stream in while the latency-bound top-k still runs.
+// Unconditional trigger, used by sp_topk_kernel only and only AFTER its own pdl_wait() (late in the kernel, before its survivor
+// sort): everything that preceded the top-k in the stream is then complete, so the next kernel (the gather) may safely read ITS
+// OTHER inputs (x) in its prologue, before its own pdl_wait() -- the x tiles stream in while the top-k finishes.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // Tail trigger (compile with -DSPK_PDL_TAIL; OFF by default): called by every thread once its main loop is
 // done; the next kernel's CTAs then launch while this kernel drains (their pdl_wait() still waits for this
@@ -162,6 +162,15 @@ __device__ __forceinline__ void pdl_tail_trigger() {
 #ifdef SPK_PDL_TAIL
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
+}
+// Per-kernel tail triggers (SPK_TAIL_MASK, one bit per kernel): the next kernel's CTAs may launch while this kernel's last
+// CTAs drain; their own pdl_wait() still waits for this kernel's completion and memory flush.
+#ifndef SPK_TAIL_MASK
+#define SPK_TAIL_MASK 0
+#endif
+template <int BIT>
+__device__ __forceinline__ void pdl_tail_trigger_bit() {
+    if ((SPK_TAIL_MASK >> BIT) & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 // (Early griddepcontrol.launch_dependents was measured twice on B200 and is NOT used: from every kernel the
 // step got slower, 107.7 vs 102.5 us -- waiting CTAs take resident slots from the persistent kernels; from
