@@ -14,10 +14,10 @@
 //      ties come out in ascending n, i.e. the stable descending order of the reference.
 // Work is O(N) + O(k log^2 k) per row instead of the full O(N log^2 N) sort the reference does.
 #include "spk_common.cuh"
+#include <stdlib.h>
 
 namespace spk {
 
-constexpr int TOPK_THREADS = 256;
 __device__ __forceinline__ int next_pow2_dev(int v) { return v <= 1 ? 1 : 1 << (32 - __clz(v - 1)); }
 
 __device__ __forceinline__ void ce_stage(uint64_t* buf, int len, int size, int stride, int tid,
@@ -37,8 +37,9 @@ __device__ __forceinline__ void stage_sync(int stride, int prev_stride) {
     if (stride >= 64 || prev_stride >= 64) __syncthreads(); else __syncwarp();
 }
 
-// exclusive prefix sum of one int per thread over the 256-thread CTA; returns the grand total
-__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot /*[8]*/, int tid, int& total) {
+// exclusive prefix sum of one int per thread over the NT-thread CTA; returns the grand total
+template <int NT>
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot /*[NT/32]*/, int tid, int& total) {
     const int lane = tid & 31, warp = tid >> 5;
     int inc = v;
 #pragma unroll
@@ -50,7 +51,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot /*[8]*/
     __syncthreads();
     int base = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < TOPK_THREADS / 32; ++w) {
+    for (int w = 0; w < NT / 32; ++w) {
         const int t = warp_tot[w];
         if (w < warp) base += t;
         tot += t;
@@ -60,15 +61,16 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot /*[8]*/
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(TOPK_THREADS)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K2, int KS, int vec_ok,
                int32_t* __restrict__ idx, float* __restrict__ sp_idx,
                int64_t* __restrict__ id_activa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw);                 // K2 survivors
     uint32_t* sk = reinterpret_cast<uint32_t*>(sel + KS);                  // E*256 keys, [e][t]
-    int* hist = reinterpret_cast<int*>(sk + (size_t)E * TOPK_THREADS);     // 3 x 8 warps x 16 bins
-    __shared__ int warp_tot[TOPK_THREADS / 32];
+    int* hist = reinterpret_cast<int*>(sk + (size_t)E * NT);     // 3 x NT/32 warps x 16 bins
+    __shared__ int warp_tot[NT / 32];
     __shared__ uint32_t cand_list[32];
     __shared__ int cand_cnt;
     __shared__ uint32_t v_final;
@@ -113,10 +115,10 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
                 const int e = e0 + 4 * u;
                 if (e < E) {
                     const bool in = n0 + e < N;                             // N%4==0: all four or none
-                    sk[(e + 0) * TOPK_THREADS + tid] = in ? order_key(v[u].x) : 0u;   // pad 0 < every real key
-                    sk[(e + 1) * TOPK_THREADS + tid] = in ? order_key(v[u].y) : 0u;
-                    sk[(e + 2) * TOPK_THREADS + tid] = in ? order_key(v[u].z) : 0u;
-                    sk[(e + 3) * TOPK_THREADS + tid] = in ? order_key(v[u].w) : 0u;
+                    sk[(e + 0) * NT + tid] = in ? order_key(v[u].x) : 0u;   // pad 0 < every real key
+                    sk[(e + 1) * NT + tid] = in ? order_key(v[u].y) : 0u;
+                    sk[(e + 2) * NT + tid] = in ? order_key(v[u].z) : 0u;
+                    sk[(e + 3) * NT + tid] = in ? order_key(v[u].w) : 0u;
                 }
             }
         }
@@ -127,11 +129,11 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
             for (int u = 0; u < 8; ++u) v[u] = __ldg(krow + min(n0 + e0 + u, N - 1));
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                if (e0 + u < E) sk[(e0 + u) * TOPK_THREADS + tid] = (n0 + e0 + u < N) ? order_key(v[u]) : 0u;
+                if (e0 + u < E) sk[(e0 + u) * NT + tid] = (n0 + e0 + u < N) ? order_key(v[u]) : 0u;
         }
     }
-    for (int i = tid; i < KS; i += TOPK_THREADS) sel[i] = 0ull;
-    for (int i = tid; i < 3 * 8 * 16; i += TOPK_THREADS) hist[i] = 0;
+    for (int i = tid; i < KS; i += NT) sel[i] = 0ull;
+    for (int i = tid; i < 3 * (NT / 32) * 16; i += NT) hist[i] = 0;
     if (tid == 0) cand_cnt = 0;
 
     // ---- argmax over the R rows for this CTA's slice of n (softpool.py:95) --------------------------
@@ -153,7 +155,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
             }
             id_activa[(size_t)b * N + s0 + tid] = (int64_t)besti;
         }
-        for (int n = s0 + tid + TOPK_THREADS; n < s1; n += TOPK_THREADS) {
+        for (int n = s0 + tid + NT; n < s1; n += NT) {
             uint32_t bestk = order_key(__ldg(kb + n));
             int besti = 0;
 #pragma unroll 8
@@ -177,10 +179,10 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     bool done_fast = false;
 #ifndef SPK_NO_TOPK_SHORTCUT
     if (k <= 32 && KS >= 256) {
-        __shared__ uint32_t warp_thr[TOPK_THREADS / 32];
+        __shared__ uint32_t warp_thr[NT / 32];
         uint32_t tmax = 0;
-        for (int e = 0; e < E; ++e) tmax = max(tmax, sk[e * TOPK_THREADS + tid]);
-        const int J = (k + 7) >> 3;
+        for (int e = 0; e < E; ++e) tmax = max(tmax, sk[e * NT + tid]);
+        const int J = (k + NT / 32 - 1) / (NT / 32);
         const int lane_ = tid & 31;
         uint32_t v = tmax, jth = 0;
         for (int j = 0; j < J; ++j) {
@@ -192,14 +194,14 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         __syncthreads();
         uint32_t T0 = warp_thr[0];
 #pragma unroll
-        for (int w = 1; w < TOPK_THREADS / 32; ++w) T0 = min(T0, warp_thr[w]);
+        for (int w = 1; w < NT / 32; ++w) T0 = min(T0, warp_thr[w]);
         int mine = 0;
-        for (int e = 0; e < E; ++e) mine += sk[e * TOPK_THREADS + tid] >= T0;
+        for (int e = 0; e < E; ++e) mine += sk[e * NT + tid] >= T0;
         int total;
-        int pos = block_exclusive_scan(mine, warp_tot, tid, total);
+        int pos = block_exclusive_scan<NT>(mine, warp_tot, tid, total);
         if (total <= KS && T0 > 0u) {                            // (T0 == 0: padding keys could be counted -> generic path)
             for (int e = 0; e < E; ++e) {
-                const uint32_t key = sk[e * TOPK_THREADS + tid];
+                const uint32_t key = sk[e * NT + tid];
                 if (key >= T0) sel[pos++] = ((uint64_t)key << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)(n0 + e));
             }
             K2s = max(2, next_pow2_dev(total));
@@ -218,11 +220,11 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     const int lane = tid & 31, warp = tid >> 5;
     for (int round = 0; round < 8 && !done_fast; ++round) {
         const int sh = 28 - 4 * round;
-        int* H = hist + (round % 3) * (8 * 16);
+        int* H = hist + (round % 3) * ((NT / 32) * 16);
         const uint32_t pre = (round == 0) ? 0u : (V >> (sh + 4));
 #pragma unroll 4
         for (int e = 0; e < E; ++e) {
-            const uint32_t key = sk[e * TOPK_THREADS + tid];
+            const uint32_t key = sk[e * NT + tid];
             const bool cand = (round == 0) || ((key >> (sh + 4)) == pre);
             if (cand) atomicAdd(&H[warp * 16 + ((key >> sh) & 15u)], 1);
         }
@@ -230,7 +232,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         int c = 0;
         if (lane < 16) {
 #pragma unroll
-            for (int w = 0; w < TOPK_THREADS / 32; ++w) c += H[w * 16 + lane];
+            for (int w = 0; w < NT / 32; ++w) c += H[w * 16 + lane];
         }
         // suffix sums over digits: S(d) = # candidates with digit >= d   (lanes >= 16 hold 0)
         int S = c;
@@ -249,8 +251,8 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         // c, S, dsel are identical in every warp, so the branch is uniform.
         if (round < 7 && __shfl_sync(0xFFFFFFFFu, c, dsel) <= 32) { fin_sh = sh; break; }
         // recycle the histogram used two rounds from now (everybody is past the barrier of the previous round)
-        int* Hz = hist + ((round + 2) % 3) * (8 * 16);
-        if (tid < 8 * 16) Hz[tid] = 0;
+        int* Hz = hist + ((round + 2) % 3) * ((NT / 32) * 16);
+        if (tid < (NT / 32) * 16) Hz[tid] = 0;
     }
 
     if (fin_sh >= 0 && !done_fast) {
@@ -258,7 +260,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         const uint32_t pre = V >> fin_sh;
 #pragma unroll 4
         for (int e = 0; e < E; ++e) {
-            const uint32_t key = sk[e * TOPK_THREADS + tid];
+            const uint32_t key = sk[e * NT + tid];
             if ((key >> fin_sh) == pre) cand_list[atomicAdd(&cand_cnt, 1)] = key;
         }
         __syncthreads();
@@ -283,19 +285,19 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     int my_gt = 0, my_eq = 0;
 #pragma unroll 4
     for (int e = 0; e < E; ++e) {
-        const uint32_t key = sk[e * TOPK_THREADS + tid];
+        const uint32_t key = sk[e * NT + tid];
         my_gt += key > V; my_eq += key == V;
     }
     // one scan for both counts: (gt << 16) | eq  (each <= E*256 <= 16384)
     int total_ge;
-    const int ge_before = block_exclusive_scan((my_gt << 16) | my_eq, warp_tot, tid, total_ge);
+    const int ge_before = block_exclusive_scan<NT>((my_gt << 16) | my_eq, warp_tot, tid, total_ge);
     const int eq_before = ge_before & 0xFFFF, total_gt = total_ge >> 16;
     const int need = k - total_gt;                       // >= 1 ties to take, lowest indices first
     // the ties taken are the first `need` in index order, so the ones before this thread are min(eq_before, need)
     int pos = (ge_before >> 16) + min(eq_before, need);
     int eq_rank = eq_before;
     for (int e = 0; e < E; ++e) {
-        const uint32_t key = sk[e * TOPK_THREADS + tid];
+        const uint32_t key = sk[e * NT + tid];
         bool take = key > V;
         if (key == V) { take = eq_rank < need; ++eq_rank; }
         if (take) { sel[pos++] = ((uint64_t)key << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)(n0 + e)); }
@@ -330,7 +332,7 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
         for (int size = 2; size <= K2s; size <<= 1)
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
                 stage_sync(stride, prev);
-                ce_stage(sel, K2s, size, stride, tid, TOPK_THREADS);
+                ce_stage(sel, K2s, size, stride, tid, NT);
                 prev = stride;
             }
     }
@@ -340,10 +342,10 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     // ---- emit ---------------------------------------------------------------------------------------------
     pdl_tail_trigger();
     int32_t* orow = idx + (size_t)row * k;
-    for (int j = tid; j < k; j += TOPK_THREADS) orow[j] = (int32_t)(0xFFFFFFFFu - (uint32_t)sel[j]);
+    for (int j = tid; j < k; j += NT) orow[j] = (int32_t)(0xFFFFFFFFu - (uint32_t)sel[j]);
     if (sp_idx != nullptr) {
         const int Q = R + 3;
-        for (int e = tid; e < Q * k; e += TOPK_THREADS) {
+        for (int e = tid; e < Q * k; e += NT) {
             const int q = e / k, j = e - q * k;
             sp_idx[(((size_t)b * Q + q) * R + r) * k + j] = (float)(0xFFFFFFFFu - (uint32_t)sel[j]);
         }
@@ -387,14 +389,24 @@ extern "C" int sp_topk_f32(const float* keys, int B, int R, int N, int k, int32_
     if (sp_idx && N >= (1 << 24)) return fail(SPK_E_UNSUPPORTED, "sp_topk_f32: N >= 2^24 not exact in float32");
     const int vec_ok = ((uintptr_t)keys & 15) == 0;     // misaligned keys: scalar loads (the gather and Chamfer kernels do the same)
     const int K2 = max(2, next_pow2(k));
-    int E = (N + TOPK_THREADS - 1) / TOPK_THREADS;
+    // CTA width: 256 threads are the fastest up to N = 8192 (measured, us at 256 / 512 / 1024 threads: N=2048 k=32 7.5 / 12.5 / 19.3,
+    // k=256 14.0 / 20.6 / 30.2; N=4096 22.2 / 26.3 / 36.4; N=8192 42.6 / 43.0 / 49.6); only the longest rows gain from 512
+    // (N=16384: 88.4 / 72.5 / 86.7)
+    int NT = N > 8192 ? 512 : 256;
+#ifdef SPK_EXPERIMENT
+    if (const char* e = getenv("SPK_TOPK_THREADS")) { const int v = atoi(e); if (v == 256 || v == 512 || v == 1024) NT = v; }
+#endif
+    int E = (N + NT - 1) / NT;
     if (E > 4) E = (E + 3) & ~3;                       // float4 path wants E % 4 == 0
     const int KS = k <= 32 ? std::max(K2, 256) : K2;       // small k: room for every key at or above the shortcut's threshold
-    const size_t smem = (size_t)KS * sizeof(uint64_t) + (size_t)E * TOPK_THREADS * sizeof(uint32_t) + 3 * 8 * 16 * sizeof(int);
-    if (smem > 48 * 1024)
-        SPK_CUDA(cudaFuncSetAttribute(sp_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SPK_CUDA(launch_k(sp_topk_kernel, dim3(B * R), dim3(TOPK_THREADS), smem, (cudaStream_t)stream, keys, R, N, k, E, K2, KS, vec_ok, idx, sp_idx, id_activa));
-    return SPK_OK;
+    const size_t smem = (size_t)KS * sizeof(uint64_t) + (size_t)E * NT * sizeof(uint32_t) + 3 * (NT / 32) * 16 * sizeof(int);
+    auto launch = [&](auto kern) -> int {
+        if (smem > 48 * 1024)
+            SPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SPK_CUDA(launch_k(kern, dim3(B * R), dim3(NT), smem, (cudaStream_t)stream, keys, R, N, k, E, K2, KS, vec_ok, idx, sp_idx, id_activa));
+        return SPK_OK;
+    };
+    return NT == 1024 ? launch(sp_topk_kernel<1024>) : NT == 512 ? launch(sp_topk_kernel<512>) : launch(sp_topk_kernel<256>);
 }
 
 extern "C" int sp_argmax_i64(const float* keys, int B, int R, int N, int64_t* id_activa, void* stream) {
