@@ -394,7 +394,7 @@ extern "C" int sp_topk_f32(const float* keys, int B, int R, int N, int k, int32_
     // (N=16384: 88.4 / 72.5 / 86.7)
     int NT = N > 8192 ? 512 : 256;
 #ifdef SPK_EXPERIMENT
-    if (const char* e = getenv("SPK_TOPK_THREADS")) { const int v = atoi(e); if (v == 256 || v == 512 || v == 1024) NT = v; }
+    if (const char* e = getenv("SPK_TOPK_THREADS")) { const int v = atoi(e); if (v == 128 || v == 256 || v == 512 || v == 1024) NT = v; }
 #endif
     int E = (N + NT - 1) / NT;
     if (E > 4) E = (E + 3) & ~3;                       // float4 path wants E % 4 == 0
@@ -406,7 +406,7 @@ extern "C" int sp_topk_f32(const float* keys, int B, int R, int N, int k, int32_
         SPK_CUDA(launch_k(kern, dim3(B * R), dim3(NT), smem, (cudaStream_t)stream, keys, R, N, k, E, K2, KS, vec_ok, idx, sp_idx, id_activa));
         return SPK_OK;
     };
-    return NT == 1024 ? launch(sp_topk_kernel<1024>) : NT == 512 ? launch(sp_topk_kernel<512>) : launch(sp_topk_kernel<256>);
+    return NT == 1024 ? launch(sp_topk_kernel<1024>) : NT == 512 ? launch(sp_topk_kernel<512>) : NT == 128 ? launch(sp_topk_kernel<128>) : launch(sp_topk_kernel<256>);
 }
 
 extern "C" int sp_argmax_i64(const float* keys, int B, int R, int N, int64_t* id_activa, void* stream) {
