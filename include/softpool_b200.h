@@ -39,7 +39,8 @@ enum {
     SPK_E_BADARG = -1,      /* null pointer / non-positive size / k > N / k < cab ...      */
     SPK_E_UNSUPPORTED = -2, /* size outside what the sm_100a kernels are built for        */
     SPK_E_WORKSPACE = -3,   /* workspace too small (see the *_workspace_bytes functions)  */
-    SPK_E_ALIGN = -4        /* a pointer is not aligned as documented                     */
+    SPK_E_ALIGN = -4,       /* a pointer is not aligned as documented                     */
+    SPK_E_INTERNAL = -5     /* SPK_CHAMFER_SELFCHECK=1 found a result that differs from the plain kernel */
 };
 
 int spk_abi_version(void);

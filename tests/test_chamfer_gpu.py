@@ -302,6 +302,23 @@ def test_multi_prediction_call_matches_separate_calls(P, B, n, m):
     torch.testing.assert_close(tg.grad, g_gt, rtol=1e-4, atol=1e-7)
 
 
+def test_selfcheck_switch_runs_clean():
+    """SPK_CHAMFER_SELFCHECK=1 (read once per process, so a subprocess): every tensor-path call re-evaluates sample 0 with the
+    plain float32 kernel and fails loudly on a difference -- the run-time guard for the filter's hardware assumption."""
+    import subprocess
+    import sys
+    code = ("import torch, sys; sys.path.insert(0, %r); from softpool_b200 import ops\n"
+            "g = torch.Generator().manual_seed(1)\n"
+            "for (B, n, m) in [(4, 2048, 2048), (2, 700, 1100), (32, 4096, 4096), (1, 2048, 16384)]:\n"
+            "    a = (torch.rand(B, n, 3, generator=g) - 0.5).cuda(); b = (torch.rand(B, m, 3, generator=g) - 0.5).cuda()\n"
+            "    ops.chamfer_forward(a, b); torch.cuda.synchronize()\n"
+            "print('selfcheck ok')\n") % ROOT
+    env = dict(os.environ, SPK_CHAMFER_SELFCHECK="1")
+    env.pop("SPK_CHAMFER_PATH", None)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "selfcheck ok" in r.stdout, r.stderr[-2000:]
+
+
 def test_random_shapes_vs_oracle():
     """40 random cloud sizes on both sides of the tensor-path threshold, ragged against the 128/1024 tiling."""
     rng = np.random.default_rng(77)
