@@ -133,7 +133,7 @@ struct SortParams {
     int stage;                           // the clouds' raw coordinates fit in shared memory next to the sort arrays
 };
 
-__device__ __forceinline__ uint32_t spread3(uint32_t v) {           // 4 bits -> every third bit
+constexpr uint32_t spread3(uint32_t v) {           // 4 bits -> every third bit
     v = (v | (v << 8)) & 0x0000F00Fu;
     v = (v | (v << 4)) & 0x000C30C3u;
     v = (v | (v << 2)) & 0x00249249u;
@@ -141,10 +141,10 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {           // 4 bits ->
 }
 // Hilbert index of a cell (Skilling's axes-to-transpose, 3 axes x SORT_BITS bits): consecutive indices are face-adjacent
 // cells, so a run of consecutive sorted points never straddles a jump of the curve (a Morton run does: its chunks came
-// out with twice the radius and twice the candidates, tools/chunk_search_estimate.py).
-__device__ __forceinline__ uint32_t hilbert_code(uint32_t x0, uint32_t x1, uint32_t x2) {
+// out with twice the radius and twice the candidates, tools/chunk_search_estimate.py).  Evaluated at COMPILE time into a
+// SORT_CELLS-entry table: computing it per point was a third of the sort kernel's instructions.
+constexpr uint32_t hilbert_of_cell(uint32_t x0, uint32_t x1, uint32_t x2) {
     constexpr uint32_t M = 1u << (SORT_BITS - 1);
-#pragma unroll
     for (uint32_t Q = M; Q > 1; Q >>= 1) {
         const uint32_t P = Q - 1;
         if (x0 & Q) x0 ^= P;
@@ -153,10 +153,20 @@ __device__ __forceinline__ uint32_t hilbert_code(uint32_t x0, uint32_t x1, uint3
     }
     x1 ^= x0; x2 ^= x1;
     uint32_t t = 0;
-#pragma unroll
     for (uint32_t Q = M; Q > 1; Q >>= 1) if (x2 & Q) t ^= Q - 1;
     x0 ^= t; x1 ^= t; x2 ^= t;
     return (spread3(x0) << 2) | (spread3(x1) << 1) | spread3(x2);
+}
+struct HilbertTable { uint16_t v[SORT_CELLS]; };
+constexpr HilbertTable make_hilbert_table() {
+    HilbertTable t{};
+    for (uint32_t i = 0; i < (uint32_t)SORT_CELLS; ++i)
+        t.v[i] = (uint16_t)hilbert_of_cell(i >> (2 * SORT_BITS), (i >> SORT_BITS) & ((1u << SORT_BITS) - 1), i & ((1u << SORT_BITS) - 1));
+    return t;
+}
+__device__ const HilbertTable g_hilbert = make_hilbert_table();
+__device__ __forceinline__ uint32_t hilbert_code(uint32_t x0, uint32_t x1, uint32_t x2) {
+    return __ldg(&g_hilbert.v[(x0 << (2 * SORT_BITS)) | (x1 << SORT_BITS) | x2]);
 }
 __device__ __forceinline__ int cell_of(float v, float lo, float inv) {
     const float t = (v - lo) * inv;
@@ -164,11 +174,21 @@ __device__ __forceinline__ int cell_of(float v, float lo, float inv) {
     return c;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+__device__ __forceinline__ float ld_peer_f32(const float* own_smem, uint32_t peer_rank) {
+    uint32_t ra; float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(own_smem)), "r"(peer_rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SORT_THREADS)
 chamfer_sort_kernel(const SortParams p) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
     __shared__ float red[12][32];
-    __shared__ float s_box[12];                  // own lo/hi, other lo/hi
+    __shared__ float s_box[14];                  // own lo/hi, other lo/hi, own / other non-finite flag
     __shared__ float s_meta[8];
     __shared__ int s_bad;
     __shared__ float s_sum;
@@ -192,22 +212,21 @@ chamfer_sort_kernel(const SortParams p) {
     float* raw = p.stage ? reinterpret_cast<float*>(perm + ((n + 7) & ~7)) : nullptr;                // 3 n
     for (int i = tid; i < SORT_CELLS; i += SORT_THREADS) hist[i] = 0;
 
-    // ---- bounding boxes of both clouds (own first), non-finite detection --------------------------------------
+    // ---- bounding box of the own cloud + non-finite detection; the other cloud's comes from the peer CTA of the cluster
+    // pair (blockIdx.x = 0 / 1 of the same sample) through distributed shared memory ------------------------------------
     int bad = 0;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const int which = c == 0 ? cl : 1 - cl;
-        const float* X = p.xyz[which] + (size_t)b * p.n[which] * 3;
-        const int cnt = p.n[which];
+    {
+        const float* X = p.xyz[cl] + (size_t)b * n * 3;
         float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
         auto upd = [&](int a, float v) { l[a] = fminf(l[a], v); h[a] = fmaxf(h[a], v); bad |= !(fabsf(v) < INFINITY); };
         int done = 0;
         if ((((uintptr_t)X) & 15) == 0) {                       // 4 points = 12 floats = 3 float4: the axis of every lane is static
-            const int steps = cnt / 4;
+            const int steps = n / 4;
             const float4* X4 = reinterpret_cast<const float4*>(X);
-            for (int st = tid; st < steps; st += SORT_THREADS) {
+#pragma unroll 2
+            for (int st = tid; st < steps; st += SORT_THREADS) {       // (two steps' loads in flight: the phase is latency-bound)
                 const float4 a = __ldg(X4 + 3 * st), b4 = __ldg(X4 + 3 * st + 1), c4 = __ldg(X4 + 3 * st + 2);
-                if (c == 0 && raw != nullptr) {
+                if (raw != nullptr) {
                     float4* r4 = reinterpret_cast<float4*>(raw) + 3 * st;
                     r4[0] = a; r4[1] = b4; r4[2] = c4;
                 }
@@ -217,9 +236,9 @@ chamfer_sort_kernel(const SortParams p) {
             }
             done = steps * 4;
         }
-        for (int i = done + tid; i < cnt; i += SORT_THREADS) {
+        for (int i = done + tid; i < n; i += SORT_THREADS) {
             const float x = __ldg(X + 3 * i), y = __ldg(X + 3 * i + 1), z = __ldg(X + 3 * i + 2);
-            if (c == 0 && raw != nullptr) { raw[3 * i] = x; raw[3 * i + 1] = y; raw[3 * i + 2] = z; }
+            if (raw != nullptr) { raw[3 * i] = x; raw[3 * i + 1] = y; raw[3 * i + 2] = z; }
             upd(0, x); upd(1, y); upd(2, z);
         }
 #pragma unroll
@@ -228,23 +247,31 @@ chamfer_sort_kernel(const SortParams p) {
                 l[a] = fminf(l[a], __shfl_xor_sync(0xFFFFFFFFu, l[a], d));
                 h[a] = fmaxf(h[a], __shfl_xor_sync(0xFFFFFFFFu, h[a], d));
             }
-            if (lane == 0) { red[6 * c + a][warp] = l[a]; red[6 * c + 3 + a][warp] = h[a]; }
+            if (lane == 0) { red[a][warp] = l[a]; red[3 + a][warp] = h[a]; }
         }
     }
     bad = __syncthreads_or(bad);
     if (warp == 0) {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {
+        for (int k = 0; k < 6; ++k) {
             float v = red[k][lane];
-            const bool is_lo = (k % 6) < 3;
             for (int d = 16; d > 0; d >>= 1) {
                 const float o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
-                v = is_lo ? fminf(v, o) : fmaxf(v, o);
+                v = k < 3 ? fminf(v, o) : fmaxf(v, o);
             }
             if (lane == 0) s_box[k] = v;
         }
+        if (lane == 0) s_box[12] = bad ? 1.f : 0.f;
+    }
+    cluster_sync_all();                                          // (also a CTA barrier) own box visible to the peer
+    if (tid < 7) {
+        const float v = ld_peer_f32(&s_box[tid == 6 ? 12 : tid], 1u - (uint32_t)cl);
+        s_box[tid == 6 ? 13 : 6 + tid] = v;
     }
     __syncthreads();
+    cluster_arrive();                                            // the matching wait sits at the kernel's exits: the peer
+                                                                 // may still be reading this CTA's box
+    bad |= s_box[13] != 0.f;
     if (tid == 0) {
         float c[3], ext = 0.f, amax = 0.f;
         for (int a = 0; a < 3; ++a) {
@@ -277,7 +304,7 @@ chamfer_sort_kernel(const SortParams p) {
     }
     __syncthreads();
     SORT_PHASE();                 // 1: bounding boxes + meta
-    if (s_bad) return;            // the search kernel walks the original arrays in reference order: nothing to sort
+    if (s_bad) { cluster_wait(); return; }   // the search kernel walks the original arrays in reference order: nothing to sort
     const float* X = raw != nullptr ? raw : p.xyz[cl] + (size_t)b * n * 3;       // (shared or global: plain loads from here on)
     const float cx = s_meta[0], cy = s_meta[1], cz = s_meta[2], sc = s_meta[3], sc2 = s_meta[5];
 
@@ -337,29 +364,41 @@ chamfer_sort_kernel(const SortParams p) {
     if (tid == 0) s_sum = 0.f;
     __syncthreads();
     float sub_sum = 0.f;
-    for (int s = tid; s < n_pad; s += SORT_THREADS) {
-        const bool real = s < n;
-        float x = INFINITY, y = INFINITY, z = INFINITY;
-        int orig = 0x7FFFFFFF;
-        if (real) {
-            orig = perm[s];
-            x = X[3 * orig]; y = X[3 * orig + 1]; z = X[3 * orig + 2];
+    // four consecutive sorted positions per thread, a chunk = 4 consecutive lanes: 14 shuffles per 128 points (one point per
+    // thread took 28 per 32, and the shuffle pipe was this phase's bound).  n_pad / 4 is a multiple of 32: whole warps.
+    for (int q = tid; q < n_pad / 4; q += SORT_THREADS) {
+        const int s0 = q * 4;
+        float x[4], y[4], z[4];
+        uint32_t pk[2] = {0u, 0u};
+        if (s0 < n) { const uint2 t = *reinterpret_cast<const uint2*>(perm + s0); pk[0] = t.x; pk[1] = t.y; }   // (perm holds (n+7)&~7 entries)
+        float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool real = s0 + j < n;
+            int orig = 0x7FFFFFFF;
+            x[j] = INFINITY; y[j] = INFINITY; z[j] = INFINITY;
+            if (real) {
+                orig = (int)((pk[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+                x[j] = X[3 * orig]; y[j] = X[3 * orig + 1]; z[j] = X[3 * orig + 2];
+                l[0] = fminf(l[0], x[j]); l[1] = fminf(l[1], y[j]); l[2] = fminf(l[2], z[j]);
+                h[0] = fmaxf(h[0], x[j]); h[1] = fmaxf(h[1], y[j]); h[2] = fmaxf(h[2], z[j]);
+            }
+            S[s0 + j] = make_float4(x[j], y[j], z[j], __int_as_float(orig));
         }
-        S[s] = make_float4(x, y, z, __int_as_float(orig));
-        // chunk = 16 consecutive lanes
-        float l[3] = {x, y, z}, h[3] = {real ? x : -INFINITY, real ? y : -INFINITY, real ? z : -INFINITY};   // (!real: x = y = z = +inf)
 #pragma unroll
         for (int a = 0; a < 3; ++a)
-            for (int d = 8; d > 0; d >>= 1) {
+            for (int d = 2; d > 0; d >>= 1) {
                 l[a] = fminf(l[a], __shfl_xor_sync(0xFFFFFFFFu, l[a], d));
                 h[a] = fmaxf(h[a], __shfl_xor_sync(0xFFFFFFFFu, h[a], d));
             }
         const float ccx = 0.5f * l[0] + 0.5f * h[0], ccy = 0.5f * l[1] + 0.5f * h[1], ccz = 0.5f * l[2] + 0.5f * h[2];
         float r2 = 0.f;
-        if (real) { const float dx = x - ccx, dy = y - ccy, dz = z - ccz; r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy)); }
-        for (int d = 8; d > 0; d >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xFFFFFFFFu, r2, d));
-        const int chunk = s >> 4;
-        if ((lane & 15) == 0 && chunk < nc) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (s0 + j < n) { const float dx = x[j] - ccx, dy = y[j] - ccy, dz = z[j] - ccz; r2 = fmaxf(r2, fmaf(dz, dz, fmaf(dx, dx, dy * dy))); }
+        for (int d = 2; d > 0; d >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xFFFFFFFFu, r2, d));
+        const int chunk = q >> 2;
+        if ((lane & 3) == 0 && chunk < nc) {
             const float sub = 1.5f * r2 * sc2 * 1.001f;          // 1.5 r^2 in scaled units, inflated for the rounding of r2 itself
             cst[chunk] = make_float4(ccx, ccy, ccz, sub);
             box[2 * chunk] = make_float4(l[0], l[1], l[2], 0.f);
@@ -403,6 +442,7 @@ chamfer_sort_kernel(const SortParams p) {
                tph[1] - tph[0], tph[2] - tph[1], tph[3] - tph[2], tph[4] - tph[3], tph[5] - tph[4], tph[6] - tph[5]);
 #endif
     pdl_tail_trigger_bit<5>();
+    cluster_wait();
 }
 
 // ---------------------------------------------------------------------------------------------
