@@ -8,10 +8,13 @@
 // the whole MMA -> commit -> tcgen05.ld -> release round trip (~600 cycles, tools/micro/tc_pipe2_bench.cu), so
 // 512 columns x 128 lanes cap an SM at ~110 pair distances per cycle whatever the kernel does.  This version
 // spends the tensor pipe on 16x fewer outputs:
-//   prep   chamfer_sort_kernel: one CTA per (sample, cloud).  Counting sort of the points by Hilbert cell
-//          (16^3 grid on the cloud's bounding box), so that CHUNK = 16 consecutive points are neighbours.  Per
-//          chunk: bounding box, centre c, radius r.  Emits the sorted points (x, y, z, original index), fp16
-//          operand rows A'(p) for every point as a QUERY and B'(c) for every CHUNK CENTRE as a target.
+//   prep   chamfer_sort_reg_kernel / chamfer_sort_kernel: one thread-block CLUSTER per sample, 1, 2 or 4 CTAs per
+//          cloud.  Counting sort of the points by Hilbert cell (16^3 grid on the cloud's bounding box), so that
+//          CHUNK = 16 consecutive points are neighbours.  Per chunk: bounding box, centre c, radius r.  Emits the
+//          sorted points (x, y, z, original index) and the fp16 operand rows B'(c) of every CHUNK CENTRE as a
+//          target (a query's row A'(p) is formatted by the search kernel).  Slices of <= 4096 points per CTA take the
+//          register kernel (points in registers, scatter through distributed shared memory, one bulk copy out);
+//          larger ones the generic kernel (scatter through global memory).
 //   search chamfer_search_kernel: a job = 128 queries of one sample and direction; per pass of 128 chunks
 //          (2048 targets) ONE M=128 x N=128 x K=16 tcgen05.mma gives, for every query, 128 values
 //              V_j = bias + |p - c_j|^2 - 1.5 r_j^2      (scaled units, fp16 accumulators)
@@ -26,6 +29,7 @@
 #include "spk_common.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace spk {
 
@@ -130,7 +134,9 @@ struct SortParams {
     ChamferGrid* grid[2];                // per sample
     ChamferMeta* meta;
     float* loss;                         // fused loss only: (B) accumulators, zeroed here
-    int stage;                           // the clouds' raw coordinates fit in shared memory next to the sort arrays
+    int cl_ctas;                         // CTAs per cloud (the cluster holds 2 * cl_ctas)
+    int pps_max;                         // points per slice of the larger cloud (shared-memory layout)
+    int cps_max;                         // chunks per slice of the larger cloud
 };
 
 constexpr uint32_t spread3(uint32_t v) {           // 4 bits -> every third bit
@@ -174,21 +180,51 @@ __device__ __forceinline__ int cell_of(float v, float lo, float inv) {
     return c;
 }
 
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
-__device__ __forceinline__ float ld_peer_f32(const float* own_smem, uint32_t peer_rank) {
-    uint32_t ra; float v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(own_smem)), "r"(peer_rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-    return v;
+// Thread 0 of every CTA of a sample's cluster: the common centre / scale / error bound of the two clouds (from their
+// boxes in s_box: own lo, own hi, other lo, other hi) -> s_meta; the first CTA also writes the sample's ChamferMeta.
+__device__ __forceinline__ void sort_write_meta(const SortParams& p, const float* s_box, float* s_meta, int* s_bad, bool writer, int b) {
+    float c[3], ext = 0.f, amax = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        const float L = fminf(s_box[a], s_box[6 + a]), H = fmaxf(s_box[3 + a], s_box[9 + a]);
+        c[a] = 0.5f * L + 0.5f * H;
+        ext = fmaxf(ext, fmaxf(H - c[a], c[a] - L));
+        amax = fmaxf(amax, fmaxf(fabsf(L), fabsf(H)));
+    }
+    // scale = 2^-ceil(log2(ext)) so that |x - c| * scale <= 1; degenerate / non-finite boxes -> 1
+    float scale = 1.f;
+    if (ext > 0.f && ext < INFINITY) {
+        int e = ((__float_as_int(ext) >> 23) & 255) - 126;       // ext = f * 2^e, f in [0.5, 1) (denormals end up at the clamp)
+        e = max(-100, min(100, e));
+        scale = __int_as_float((127 - e) << 23);
+    }
+    // error budget of V in scaled units: fp16 hi/lo products + fp32-grade accumulation (2^-17) plus the rounding
+    // of the centred coordinates themselves (|x| * 2^-23 * scale each)
+    const float delta = amax * scale * 1.1920929e-7f;
+    const float e_tot = 7.62939453125e-6f + 16.f * delta;
+    // the bias of the chunk rows (a power of two <= 1024) must stay above the radius cap + error bound
+    const bool hopeless = !(TC_RCAP_MAX + 4.f * e_tot <= 1024.f) || !(scale * scale > 0.f) || !(scale * scale < INFINITY);
+    s_meta[0] = c[0]; s_meta[1] = c[1]; s_meta[2] = c[2]; s_meta[3] = scale; s_meta[4] = 2.f * e_tot; s_meta[5] = scale * scale;
+    const int sb = (*s_bad || hopeless) ? 1 : 0;
+    *s_bad = sb;
+    if (writer) {
+        ChamferMeta mm; mm.cx = c[0]; mm.cy = c[1]; mm.cz = c[2]; mm.scale = scale; mm.tau = 2.f * e_tot;
+        mm.scale2 = scale * scale; mm.bias = 0.f; mm.nonfinite = sb ? 1.f : 0.f;
+        p.meta[b] = mm;
+        if (p.loss != nullptr) p.loss[b] = 0.f;
+    }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SORT_THREADS)
+// One thread-block CLUSTER per sample: 2 clouds x CL CTAs (CL = p.cl_ctas = 1, 2 or 4, chosen so that the grid covers the
+// machine once).  A cloud's CTA h owns the h-th slice of its POINTS for the bounding box, the cell histogram and the
+// scatter, and the h-th slice of its CHUNKS for the chunk statistics and operand rows; partial boxes, cell counters and
+// radius sums travel through distributed shared memory, the sorted points through global memory (visible cluster-wide
+// after the release/acquire cluster barrier).
+__global__ void __launch_bounds__(SORT_THREADS)
 chamfer_sort_kernel(const SortParams p) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
-    __shared__ float red[12][32];
-    __shared__ float s_box[14];                  // own lo/hi, other lo/hi, own / other non-finite flag
+    __shared__ float red[6][32];
+    __shared__ float s_part[8];                  // read by the peers: slice lo[3], hi[3], non-finite flag, chunk radius sum
+    __shared__ float s_box[12];                  // own cloud lo/hi, other cloud lo/hi
     __shared__ float s_meta[8];
     __shared__ int s_bad;
     __shared__ float s_sum;
@@ -201,53 +237,53 @@ chamfer_sort_kernel(const SortParams p) {
 #else
 #define SORT_PHASE()
 #endif
-    const int cl = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int CL = p.cl_ctas;
+    const int crank = blockIdx.x;                // == %cluster_ctarank: the cluster spans the grid's x extent
+    const int cl = crank / CL, h = crank - cl * CL, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     SORT_PHASE();
     const int n = p.n[cl], n_pad = p.n_pad[cl], nc = p.nc[cl], nc_pad = p.nc_pad[cl];
-    uint32_t* hist = reinterpret_cast<uint32_t*>(sort_smem);                              // SORT_CELLS
-    uint32_t* cellrank = hist + SORT_CELLS;                                                  // n
-    uint16_t* perm = reinterpret_cast<uint16_t*>(cellrank + ((n + 3) & ~3));                 // n
-    // the cloud's raw coordinates, staged by the bounding-box pass when they fit (the later phases then never wait for
-    // global memory: cells + histogram 3.8k -> cycles, sorted rows 9.1k -> at n = 2048)
-    float* raw = p.stage ? reinterpret_cast<float*>(perm + ((n + 7) & ~7)) : nullptr;                // 3 n
+    const int pps = (((n + CL - 1) / CL) + 3) & ~3;                 // points per slice (multiple of 4: keeps the float4 path aligned)
+    const int i0 = min(n, h * pps), i1 = min(n, i0 + pps);
+    const int nch = n_pad / TC_CHUNK;                               // chunks that hold points or tile padding (multiple of 8)
+    const int cps = (((nch + CL - 1) / CL) + 7) & ~7;               // chunks per slice (multiple of 8: whole warps below)
+    const int c0 = min(nch, h * cps), c1 = min(nch, c0 + cps);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sort_smem);        // SORT_CELLS: this slice's points per cell
+    uint32_t* base = hist + SORT_CELLS;                             // SORT_CELLS: first sorted position of this slice's points per cell
+    uint32_t* cellrank = base + SORT_CELLS;                         // pps: (cell << 16) | rank inside (slice, cell)
+    float4* cst = reinterpret_cast<float4*>(cellrank + p.pps_max);  // cps: per chunk (centre, 1.5 r^2 scaled)
+    const float* X = p.xyz[cl] + (size_t)b * n * 3;
     for (int i = tid; i < SORT_CELLS; i += SORT_THREADS) hist[i] = 0;
 
-    // ---- bounding box of the own cloud + non-finite detection; the other cloud's comes from the peer CTA of the cluster
-    // pair (blockIdx.x = 0 / 1 of the same sample) through distributed shared memory ------------------------------------
+    // ---- bounding box of the slice + non-finite detection -------------------------------------------------------------
     int bad = 0;
     {
-        const float* X = p.xyz[cl] + (size_t)b * n * 3;
-        float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
-        auto upd = [&](int a, float v) { l[a] = fminf(l[a], v); h[a] = fmaxf(h[a], v); bad |= !(fabsf(v) < INFINITY); };
+        const float* Xs = X + (size_t)3 * i0;
+        const int cnt = i1 - i0;
+        float l[3] = {INFINITY, INFINITY, INFINITY}, hh[3] = {-INFINITY, -INFINITY, -INFINITY};
+        auto upd = [&](int a, float v) { l[a] = fminf(l[a], v); hh[a] = fmaxf(hh[a], v); bad |= !(fabsf(v) < INFINITY); };
         int done = 0;
-        if ((((uintptr_t)X) & 15) == 0) {                       // 4 points = 12 floats = 3 float4: the axis of every lane is static
-            const int steps = n / 4;
-            const float4* X4 = reinterpret_cast<const float4*>(X);
+        if ((((uintptr_t)Xs) & 15) == 0) {                      // 4 points = 12 floats = 3 float4: the axis of every lane is static
+            const int steps = cnt / 4;
+            const float4* X4 = reinterpret_cast<const float4*>(Xs);
 #pragma unroll 2
             for (int st = tid; st < steps; st += SORT_THREADS) {       // (two steps' loads in flight: the phase is latency-bound)
                 const float4 a = __ldg(X4 + 3 * st), b4 = __ldg(X4 + 3 * st + 1), c4 = __ldg(X4 + 3 * st + 2);
-                if (raw != nullptr) {
-                    float4* r4 = reinterpret_cast<float4*>(raw) + 3 * st;
-                    r4[0] = a; r4[1] = b4; r4[2] = c4;
-                }
                 upd(0, a.x); upd(1, a.y); upd(2, a.z); upd(0, a.w);
                 upd(1, b4.x); upd(2, b4.y); upd(0, b4.z); upd(1, b4.w);
                 upd(2, c4.x); upd(0, c4.y); upd(1, c4.z); upd(2, c4.w);
             }
             done = steps * 4;
         }
-        for (int i = done + tid; i < n; i += SORT_THREADS) {
-            const float x = __ldg(X + 3 * i), y = __ldg(X + 3 * i + 1), z = __ldg(X + 3 * i + 2);
-            if (raw != nullptr) { raw[3 * i] = x; raw[3 * i + 1] = y; raw[3 * i + 2] = z; }
-            upd(0, x); upd(1, y); upd(2, z);
+        for (int i = done + tid; i < cnt; i += SORT_THREADS) {
+            upd(0, __ldg(Xs + 3 * i)); upd(1, __ldg(Xs + 3 * i + 1)); upd(2, __ldg(Xs + 3 * i + 2));
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             for (int d = 16; d > 0; d >>= 1) {
                 l[a] = fminf(l[a], __shfl_xor_sync(0xFFFFFFFFu, l[a], d));
-                h[a] = fmaxf(h[a], __shfl_xor_sync(0xFFFFFFFFu, h[a], d));
+                hh[a] = fmaxf(hh[a], __shfl_xor_sync(0xFFFFFFFFu, hh[a], d));
             }
-            if (lane == 0) { red[a][warp] = l[a]; red[3 + a][warp] = h[a]; }
+            if (lane == 0) { red[a][warp] = l[a]; red[3 + a][warp] = hh[a]; }
         }
     }
     bad = __syncthreads_or(bad);
@@ -259,56 +295,33 @@ chamfer_sort_kernel(const SortParams p) {
                 const float o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
                 v = k < 3 ? fminf(v, o) : fmaxf(v, o);
             }
-            if (lane == 0) s_box[k] = v;
+            if (lane == 0) s_part[k] = v;
         }
-        if (lane == 0) s_box[12] = bad ? 1.f : 0.f;
+        if (lane == 0) s_part[6] = bad ? 1.f : 0.f;
     }
-    cluster_sync_all();                                          // (also a CTA barrier) own box visible to the peer
-    if (tid < 7) {
-        const float v = ld_peer_f32(&s_box[tid == 6 ? 12 : tid], 1u - (uint32_t)cl);
-        s_box[tid == 6 ? 13 : 6 + tid] = v;
+    cluster_sync_all();                                          // #1 (also a CTA barrier): every slice's box is published
+    if (tid < 12) {                                              // 0..5 own cloud, 6..11 other cloud
+        const int which = tid < 6 ? cl : 1 - cl, k = tid < 6 ? tid : tid - 6;
+        float v = k < 3 ? INFINITY : -INFINITY;
+        for (int r = 0; r < CL; ++r) {
+            const float o = ld_peer_f32(&s_part[k], (uint32_t)(which * CL + r));
+            v = k < 3 ? fminf(v, o) : fmaxf(v, o);
+        }
+        s_box[tid] = v;
+    } else if (tid == 32) {
+        int any = 0;
+        for (int r = 0; r < 2 * CL; ++r) any |= ld_peer_f32(&s_part[6], (uint32_t)r) != 0.f;
+        s_bad = any;
     }
     __syncthreads();
-    cluster_arrive();                                            // the matching wait sits at the kernel's exits: the peer
-                                                                 // may still be reading this CTA's box
-    bad |= s_box[13] != 0.f;
-    if (tid == 0) {
-        float c[3], ext = 0.f, amax = 0.f;
-        for (int a = 0; a < 3; ++a) {
-            const float L = fminf(s_box[a], s_box[6 + a]), H = fmaxf(s_box[3 + a], s_box[9 + a]);
-            c[a] = 0.5f * L + 0.5f * H;
-            ext = fmaxf(ext, fmaxf(H - c[a], c[a] - L));
-            amax = fmaxf(amax, fmaxf(fabsf(L), fabsf(H)));
-        }
-        // scale = 2^-ceil(log2(ext)) so that |x - c| * scale <= 1; degenerate / non-finite boxes -> 1
-        float scale = 1.f;
-        if (ext > 0.f && ext < INFINITY) {
-            int e = ((__float_as_int(ext) >> 23) & 255) - 126;       // ext = f * 2^e, f in [0.5, 1) (denormals end up at the clamp)
-            e = max(-100, min(100, e));
-            scale = __int_as_float((127 - e) << 23);
-        }
-        // error budget of V in scaled units: fp16 hi/lo products + fp32-grade accumulation (2^-17) plus the rounding
-        // of the centred coordinates themselves (|x| * 2^-23 * scale each)
-        const float delta = amax * scale * 1.1920929e-7f;
-        const float e_tot = 7.62939453125e-6f + 16.f * delta;
-        // the bias of the chunk rows (a power of two <= 1024) must stay above the radius cap + error bound
-        const bool hopeless = !(TC_RCAP_MAX + 4.f * e_tot <= 1024.f) || !(scale * scale > 0.f) || !(scale * scale < INFINITY);
-        s_meta[0] = c[0]; s_meta[1] = c[1]; s_meta[2] = c[2]; s_meta[3] = scale; s_meta[4] = 2.f * e_tot; s_meta[5] = scale * scale;
-        s_bad = (bad || hopeless) ? 1 : 0;
-        if (cl == 0) {
-            ChamferMeta mm; mm.cx = c[0]; mm.cy = c[1]; mm.cz = c[2]; mm.scale = scale; mm.tau = 2.f * e_tot;
-            mm.scale2 = scale * scale; mm.bias = 0.f; mm.nonfinite = s_bad ? 1.f : 0.f;
-            p.meta[b] = mm;
-            if (p.loss != nullptr) p.loss[b] = 0.f;
-        }
-    }
+    if (tid == 0) sort_write_meta(p, s_box, s_meta, &s_bad, crank == 0, b);
     __syncthreads();
     SORT_PHASE();                 // 1: bounding boxes + meta
-    if (s_bad) { cluster_wait(); return; }   // the search kernel walks the original arrays in reference order: nothing to sort
-    const float* X = raw != nullptr ? raw : p.xyz[cl] + (size_t)b * n * 3;       // (shared or global: plain loads from here on)
+    // every CTA of the cluster takes the same decision (same inputs); the peers may still be reading s_part
+    if (s_bad) { cluster_sync_all(); return; }   // the search kernel walks the original arrays in reference order: nothing to sort
     const float cx = s_meta[0], cy = s_meta[1], cz = s_meta[2], sc = s_meta[3], sc2 = s_meta[5];
 
-    // ---- counting sort by Morton cell of the cloud's own bounding box --------------------------------------------
+    // ---- counting sort by Hilbert cell of the cloud's own bounding box: this slice's counters -------------------------
     float inv[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -316,19 +329,26 @@ chamfer_sort_kernel(const SortParams p) {
         inv[a] = e > 0.f ? (float)(1 << SORT_BITS) / e : 0.f;
         if (!(inv[a] < INFINITY)) inv[a] = 0.f;
     }
-    for (int i = tid; i < n; i += SORT_THREADS) {
-        const float x = X[3 * i], y = X[3 * i + 1], z = X[3 * i + 2];
+    for (int i = i0 + tid; i < i1; i += SORT_THREADS) {
+        const float x = __ldg(X + 3 * i), y = __ldg(X + 3 * i + 1), z = __ldg(X + 3 * i + 2);
         const uint32_t code = hilbert_code((uint32_t)cell_of(x, s_box[0], inv[0]), (uint32_t)cell_of(y, s_box[1], inv[1]), (uint32_t)cell_of(z, s_box[2], inv[2]));
         const uint32_t rank = atomicAdd(&hist[code], 1u);
-        cellrank[i] = (code << 16) | rank;
+        cellrank[i - i0] = (code << 16) | rank;
     }
-    __syncthreads();
+    cluster_sync_all();                                          // #2: every slice's counters are final
     SORT_PHASE();                 // 2: cells + histogram
-    {   // exclusive scan of the SORT_CELLS counters: SORT_CELLS / SORT_THREADS consecutive cells per thread
+    {   // exclusive scan of the cloud's SORT_CELLS counters (sum over its slices): SORT_CELLS / SORT_THREADS consecutive
+        // cells per thread.  Inside a cell the slices' points follow each other in slice order.
         constexpr int PER = SORT_CELLS / SORT_THREADS;
-        uint32_t v[PER], sum = 0;
+        static_assert(PER == 4, "one 16-byte read of the peers' counters per thread");
+        uint32_t v[PER] = {0u, 0u, 0u, 0u}, lower[PER] = {0u, 0u, 0u, 0u}, sum = 0;
+        for (int r = 0; r < CL; ++r) {
+            const uint4 c = (r == h) ? *reinterpret_cast<const uint4*>(hist + tid * PER) : ld_peer_u4(hist + tid * PER, (uint32_t)(cl * CL + r));
+            v[0] += c.x; v[1] += c.y; v[2] += c.z; v[3] += c.w;
+            if (r < h) { lower[0] += c.x; lower[1] += c.y; lower[2] += c.z; lower[3] += c.w; }
+        }
 #pragma unroll
-        for (int k = 0; k < PER; ++k) { v[k] = hist[tid * PER + k]; sum += v[k]; }
+        for (int k = 0; k < PER; ++k) sum += v[k];
         uint32_t incl = sum;
         for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
         if (lane == 31) warp_tot[warp] = incl;
@@ -340,58 +360,54 @@ chamfer_sort_kernel(const SortParams p) {
         }
         __syncthreads();
         uint32_t run = warp_tot[warp] + incl - sum;
+        uint32_t st4[PER];
 #pragma unroll
-        for (int k = 0; k < PER; ++k) { hist[tid * PER + k] = run; run += v[k]; }
+        for (int k = 0; k < PER; ++k) { st4[k] = run; base[tid * PER + k] = run + lower[k]; run += v[k]; }
+        if (h == 0) {   // the search kernel starts every query at the chunk of its own cell ("home" chunk)
+            uint16_t* cs = p.cellstart[cl] + (size_t)b * SORT_CELLS;
+            *reinterpret_cast<uint2*>(cs + tid * PER) = make_uint2(st4[0] | (st4[1] << 16), st4[2] | (st4[3] << 16));
+        }
     }
     __syncthreads();
-    SORT_PHASE();                 // 3: scan
-    {   // the search kernel starts every query at the chunk of its own cell ("home" chunk)
-        uint16_t* cs = p.cellstart[cl] + (size_t)b * SORT_CELLS;
-        for (int i = tid; i < SORT_CELLS; i += SORT_THREADS) cs[i] = (uint16_t)hist[i];
-    }
-    for (int i = tid; i < n; i += SORT_THREADS) {
-        const uint32_t cr = cellrank[i];
-        perm[hist[cr >> 16] + (cr & 0xFFFFu)] = (uint16_t)i;
-    }
-    __syncthreads();
-
-    SORT_PHASE();                 // 4: cell starts + permutation
-    // ---- sorted outputs: points, query operand rows, per-chunk box / centre / radius ------------------------------------
+    SORT_PHASE();                 // 3: scan + cell starts
     float4* S = p.S[cl] + (size_t)b * nc_pad * TC_CHUNK;
+    for (int i = i0 + tid; i < i1; i += SORT_THREADS) {          // the slice's points go straight to their sorted rows
+        const uint32_t cr = cellrank[i - i0];
+        const float x = __ldg(X + 3 * i), y = __ldg(X + 3 * i + 1), z = __ldg(X + 3 * i + 2);
+        S[base[cr >> 16] + (cr & 0xFFFFu)] = make_float4(x, y, z, __int_as_float(i));
+    }
+    if (tid == 0) s_sum = 0.f;
+    cluster_sync_all();                                          // #3: the cloud's sorted rows are complete (global memory, cluster scope)
+    SORT_PHASE();                 // 4: scatter
+    // ---- this CTA's chunks: tile padding rows, per-chunk box / centre / radius -----------------------------------------
     unsigned char* Bc = p.Bc[cl] + (size_t)b * nc_pad * 32;
     float4* box = p.box[cl] + (size_t)b * nc_pad * 2;
-    float4* cst = reinterpret_cast<float4*>(cellrank);          // per chunk (centre, 1.5 r^2 scaled); cellrank is dead: n * 4 >= nc * 16 bytes
-    if (tid == 0) s_sum = 0.f;
-    __syncthreads();
     float sub_sum = 0.f;
     // four consecutive sorted positions per thread, a chunk = 4 consecutive lanes: 14 shuffles per 128 points (one point per
-    // thread took 28 per 32, and the shuffle pipe was this phase's bound).  n_pad / 4 is a multiple of 32: whole warps.
-    for (int q = tid; q < n_pad / 4; q += SORT_THREADS) {
+    // thread took 28 per 32).  4 (c1 - c0) is a multiple of 32: whole warps.
+    for (int q = 4 * c0 + tid; q < 4 * c1; q += SORT_THREADS) {
         const int s0 = q * 4;
         float x[4], y[4], z[4];
-        uint32_t pk[2] = {0u, 0u};
-        if (s0 < n) { const uint2 t = *reinterpret_cast<const uint2*>(perm + s0); pk[0] = t.x; pk[1] = t.y; }   // (perm holds (n+7)&~7 entries)
-        float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+        float l[3] = {INFINITY, INFINITY, INFINITY}, hh[3] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const bool real = s0 + j < n;
-            int orig = 0x7FFFFFFF;
             x[j] = INFINITY; y[j] = INFINITY; z[j] = INFINITY;
-            if (real) {
-                orig = (int)((pk[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
-                x[j] = X[3 * orig]; y[j] = X[3 * orig + 1]; z[j] = X[3 * orig + 2];
-                l[0] = fminf(l[0], x[j]); l[1] = fminf(l[1], y[j]); l[2] = fminf(l[2], z[j]);
-                h[0] = fmaxf(h[0], x[j]); h[1] = fmaxf(h[1], y[j]); h[2] = fmaxf(h[2], z[j]);
+            if (s0 + j < n) {
+                const float4 t = __ldcg(S + s0 + j);
+                x[j] = t.x; y[j] = t.y; z[j] = t.z;
+                l[0] = fminf(l[0], t.x); l[1] = fminf(l[1], t.y); l[2] = fminf(l[2], t.z);
+                hh[0] = fmaxf(hh[0], t.x); hh[1] = fmaxf(hh[1], t.y); hh[2] = fmaxf(hh[2], t.z);
+            } else {
+                S[s0 + j] = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0x7FFFFFFF));
             }
-            S[s0 + j] = make_float4(x[j], y[j], z[j], __int_as_float(orig));
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a)
             for (int d = 2; d > 0; d >>= 1) {
                 l[a] = fminf(l[a], __shfl_xor_sync(0xFFFFFFFFu, l[a], d));
-                h[a] = fmaxf(h[a], __shfl_xor_sync(0xFFFFFFFFu, h[a], d));
+                hh[a] = fmaxf(hh[a], __shfl_xor_sync(0xFFFFFFFFu, hh[a], d));
             }
-        const float ccx = 0.5f * l[0] + 0.5f * h[0], ccy = 0.5f * l[1] + 0.5f * h[1], ccz = 0.5f * l[2] + 0.5f * h[2];
+        const float ccx = 0.5f * l[0] + 0.5f * hh[0], ccy = 0.5f * l[1] + 0.5f * hh[1], ccz = 0.5f * l[2] + 0.5f * hh[2];
         float r2 = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -400,16 +416,25 @@ chamfer_sort_kernel(const SortParams p) {
         const int chunk = q >> 2;
         if ((lane & 3) == 0 && chunk < nc) {
             const float sub = 1.5f * r2 * sc2 * 1.001f;          // 1.5 r^2 in scaled units, inflated for the rounding of r2 itself
-            cst[chunk] = make_float4(ccx, ccy, ccz, sub);
+            cst[chunk - c0] = make_float4(ccx, ccy, ccz, sub);
             box[2 * chunk] = make_float4(l[0], l[1], l[2], 0.f);
-            box[2 * chunk + 1] = make_float4(h[0], h[1], h[2], 0.f);
+            box[2 * chunk + 1] = make_float4(hh[0], hh[1], hh[2], 0.f);
             sub_sum += fminf(sub, 4.f);
         }
     }
     for (int d = 16; d > 0; d >>= 1) sub_sum += __shfl_xor_sync(0xFFFFFFFFu, sub_sum, d);
     if (lane == 0 && sub_sum != 0.f) atomicAdd(&s_sum, sub_sum);
     __syncthreads();
-    SORT_PHASE();                 // 5: sorted points, query rows, chunk stats
+    if (tid == 0) s_part[7] = s_sum;
+    cluster_sync_all();                                          // #4: every slice's radius sum is published
+    if (tid == 0) {
+        float t = 0.f;
+        for (int r = 0; r < CL; ++r) t += ld_peer_f32(&s_part[7], (uint32_t)(cl * CL + r));    // same order in every CTA of the cloud
+        s_sum = t;
+    }
+    __syncthreads();
+    cluster_arrive();             // (the matching wait is the kernel's last statement: peers may still be reading s_part)
+    SORT_PHASE();                 // 5: chunk stats
     // ---- chunk operand rows.  The radius term folded into a row is capped at 3x the cloud's mean (outliers: chunks that
     // straddle a sparse region) -- capped chunks are flagged and always go to the box test -- and the bias, a power of two
     // above the cap + error bound, keeps every V a POSITIVE fp16 (its bit pattern then orders like its value).
@@ -417,31 +442,326 @@ chamfer_sort_kernel(const SortParams p) {
     const float e4 = 2.f * s_meta[4];                             // 4 e_tot
     float bias = 1.f / 64.f;
     while (bias < cap + e4 && bias < 1024.f) bias *= 2.f;
-    if (tid == 0) {
+    if (tid == 0 && h == 0) {
         ChamferGrid gi;
         for (int a = 0; a < 3; ++a) { gi.lo[a] = s_box[a]; gi.inv[a] = inv[a]; }
         gi.bias = bias; gi.pad = 0.f;
         p.grid[cl][b] = gi;
     }
-    for (int c = tid; c < nc_pad; c += SORT_THREADS) {
+    auto pad_chunk = [&](int c) {
+        write_b_row(Bc, c, false, 0.f, 0.f, 0.f, 0.f, 0.f);
+        box[2 * c] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
+        box[2 * c + 1] = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+    };
+    for (int c = c0 + tid; c < c1; c += SORT_THREADS) {
         if (c < nc) {
-            const float4 ci = cst[c];
+            const float4 ci = cst[c - c0];
             const bool capped = !(ci.w <= cap);
             write_b_row(Bc, c, true, (ci.x - cx) * sc, (ci.y - cy) * sc, (ci.z - cz) * sc, capped ? cap : ci.w, bias);
             if (capped) box[2 * c].w = 1.f;
         } else {
-            write_b_row(Bc, c, false, 0.f, 0.f, 0.f, 0.f, 0.f);
-            box[2 * c] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
-            box[2 * c + 1] = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+            pad_chunk(c);
         }
     }
+    for (int c = nch + h * SORT_THREADS + tid; c < nc_pad; c += CL * SORT_THREADS) pad_chunk(c);   // whole-pass padding
     SORT_PHASE();                 // 6: chunk rows
 #ifdef SPK_TIMING
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
-        printf("sort kernel phases (cycles): bbox+meta %lld, cells+hist %lld, scan %lld, perm %lld, sorted rows %lld, chunk rows %lld\n",
-               tph[1] - tph[0], tph[2] - tph[1], tph[3] - tph[2], tph[4] - tph[3], tph[5] - tph[4], tph[6] - tph[5]);
+        printf("sort kernel phases (cycles, %d CTAs per cloud): bbox+meta %lld, cells+hist %lld, scan %lld, scatter %lld, chunk stats %lld, chunk rows %lld\n",
+               CL, tph[1] - tph[0], tph[2] - tph[1], tph[3] - tph[2], tph[4] - tph[3], tph[5] - tph[4], tph[6] - tph[5]);
 #endif
     pdl_tail_trigger_bit<5>();
+    cluster_wait();
+}
+
+// The same sort for slices of at most SORT_THREADS * 4 points (clouds of up to 16384 points with 4 CTAs each): every
+// thread keeps its four points in REGISTERS from the one global read to the scatter, the Hilbert table sits in shared
+// memory, and the scatter goes through distributed shared memory straight into the CTA that owns the sorted position --
+// which then holds its slice of the sorted cloud in shared memory, writes it out with one bulk copy and computes the
+// chunk statistics from it.  (In chamfer_sort_kernel the phases were bound by the latency of re-reading the points and
+// of the round trip of the sorted rows through global memory, not by their work.)
+__global__ void __launch_bounds__(SORT_THREADS)
+chamfer_sort_reg_kernel(const SortParams p) {
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    __shared__ float red[6][32];
+    __shared__ float s_part[8];                  // read by the peers: slice lo[3], hi[3], non-finite flag, chunk radius sum
+    __shared__ float s_box[12];                  // own cloud lo/hi, other cloud lo/hi
+    __shared__ float s_meta[8];
+    __shared__ int s_bad;
+    __shared__ float s_sum;
+    __shared__ uint32_t warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int CL = p.cl_ctas;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sort_smem);        // SORT_CELLS: this slice's points per cell
+    uint32_t* base = hist + SORT_CELLS;                             // SORT_CELLS: first sorted position of this slice's points per cell
+    uint16_t* tab = reinterpret_cast<uint16_t*>(base + SORT_CELLS); // SORT_CELLS: Hilbert index of a cell
+    float4* srt = reinterpret_cast<float4*>(tab + SORT_CELLS);      // cps_max * 16: this CTA's slice of the sorted cloud
+    float4* cst = srt + (size_t)p.cps_max * TC_CHUNK;               // cps_max: per chunk (centre, 1.5 r^2 scaled)
+    pdl_trigger();
+    {   // constants and zeroing: before the wait on the previous kernel
+        static_assert(SORT_CELLS == SORT_THREADS * 4, "one 8-byte table read and four counters per thread");
+        reinterpret_cast<uint2*>(tab)[tid] = __ldg(reinterpret_cast<const uint2*>(g_hilbert.v) + tid);
+        reinterpret_cast<uint4*>(hist)[tid] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    pdl_wait();
+#ifdef SPK_TIMING
+    long long tph[8]; int nph = 0;
+    long long tf[8]; int nf = 0;
+#define RT() do { tf[nf++] = clock64(); } while (0)
+#else
+#define RT()
+#endif
+    const int crank = blockIdx.x;                // == %cluster_ctarank: the cluster spans the grid's x extent
+    const int cl = crank / CL, h = crank - cl * CL, b = blockIdx.y;
+    SORT_PHASE();
+    const int n = p.n[cl], n_pad = p.n_pad[cl], nc = p.nc[cl], nc_pad = p.nc_pad[cl];
+    const int pps = (((n + CL - 1) / CL) + 3) & ~3;                 // points per slice (<= 4 SORT_THREADS, host-checked)
+    const int i0 = min(n, h * pps), i1 = min(n, i0 + pps);
+    const int nch = n_pad / TC_CHUNK;                               // chunks that hold points or tile padding (multiple of 8)
+    const int cps = (((nch + CL - 1) / CL) + 7) & ~7;               // chunks per slice (multiple of 8: whole warps below)
+    const int c0 = min(nch, h * cps), c1 = min(nch, c0 + cps);
+    const float* X = p.xyz[cl] + (size_t)b * n * 3;
+
+    // ---- the thread's four points, bounding box of the slice, non-finite detection ---------------------------------------
+    float px[4], py[4], pz[4];
+    const int k0 = 4 * tid;                                         // first of them inside the slice
+    const int nv = max(0, min(4, i1 - i0 - k0));
+    {
+        const float* Xs = X + (size_t)3 * (i0 + k0);
+        if (nv == 4 && (((uintptr_t)Xs) & 15) == 0) {
+            const float4* X4 = reinterpret_cast<const float4*>(Xs);
+            const float4 a = __ldg(X4), b4 = __ldg(X4 + 1), c4 = __ldg(X4 + 2);
+            px[0] = a.x; py[0] = a.y; pz[0] = a.z; px[1] = a.w; py[1] = b4.x; pz[1] = b4.y;
+            px[2] = b4.z; py[2] = b4.w; pz[2] = c4.x; px[3] = c4.y; py[3] = c4.z; pz[3] = c4.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < nv) { px[j] = __ldg(Xs + 3 * j); py[j] = __ldg(Xs + 3 * j + 1); pz[j] = __ldg(Xs + 3 * j + 2); }
+                else { px[j] = 0.f; py[j] = 0.f; pz[j] = 0.f; }
+        }
+    }
+    int bad = 0;
+    {
+        float l[3] = {INFINITY, INFINITY, INFINITY}, hh[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nv) {
+                l[0] = fminf(l[0], px[j]); l[1] = fminf(l[1], py[j]); l[2] = fminf(l[2], pz[j]);
+                hh[0] = fmaxf(hh[0], px[j]); hh[1] = fmaxf(hh[1], py[j]); hh[2] = fmaxf(hh[2], pz[j]);
+                bad |= !(fabsf(px[j]) < INFINITY) | !(fabsf(py[j]) < INFINITY) | !(fabsf(pz[j]) < INFINITY);
+            }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            for (int d = 16; d > 0; d >>= 1) {
+                l[a] = fminf(l[a], __shfl_xor_sync(0xFFFFFFFFu, l[a], d));
+                hh[a] = fmaxf(hh[a], __shfl_xor_sync(0xFFFFFFFFu, hh[a], d));
+            }
+            if (lane == 0) { red[a][warp] = l[a]; red[3 + a][warp] = hh[a]; }
+        }
+    }
+    bad = __syncthreads_or(bad);
+    if (warp < 6) {                                              // one warp per component
+        float v = red[warp][lane];
+        for (int d = 16; d > 0; d >>= 1) {
+            const float o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+            v = warp < 3 ? fminf(v, o) : fmaxf(v, o);
+        }
+        if (lane == 0) s_part[warp] = v;
+    } else if (tid == 6 * 32) {
+        s_part[6] = bad ? 1.f : 0.f;
+    }
+    cluster_sync_all();                                          // #1 (also a CTA barrier): every slice's box is published
+    if (tid < 12) {                                              // 0..5 own cloud, 6..11 other cloud
+        const int which = tid < 6 ? cl : 1 - cl, k = tid < 6 ? tid : tid - 6;
+        float v = k < 3 ? INFINITY : -INFINITY;
+        for (int r = 0; r < CL; ++r) {
+            const float o = ld_peer_f32(&s_part[k], (uint32_t)(which * CL + r));
+            v = k < 3 ? fminf(v, o) : fmaxf(v, o);
+        }
+        s_box[tid] = v;
+    } else if (tid == 32) {
+        int any = 0;
+        for (int r = 0; r < 2 * CL; ++r) any |= ld_peer_f32(&s_part[6], (uint32_t)r) != 0.f;
+        s_bad = any;
+    }
+    __syncthreads();
+    if (tid == 0) sort_write_meta(p, s_box, s_meta, &s_bad, crank == 0, b);
+    __syncthreads();
+    SORT_PHASE();                 // 1: bounding boxes + meta
+    // every CTA of the cluster takes the same decision (same inputs); the peers may still be reading s_part
+    if (s_bad) { cluster_sync_all(); return; }   // the search kernel walks the original arrays in reference order: nothing to sort
+    const float cx = s_meta[0], cy = s_meta[1], cz = s_meta[2], sc = s_meta[3], sc2 = s_meta[5];
+
+    // ---- counting sort by Hilbert cell of the cloud's own bounding box: this slice's counters -------------------------
+    float inv[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float e = s_box[3 + a] - s_box[a];
+        inv[a] = e > 0.f ? (float)(1 << SORT_BITS) / e : 0.f;
+        if (!(inv[a] < INFINITY)) inv[a] = 0.f;
+    }
+    uint32_t cr[4];                                              // (cell << 16) | rank inside (slice, cell)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        cr[j] = 0;
+        if (j < nv) {
+            const uint32_t cell = ((uint32_t)cell_of(px[j], s_box[0], inv[0]) << (2 * SORT_BITS)) | ((uint32_t)cell_of(py[j], s_box[1], inv[1]) << SORT_BITS) |
+                                  (uint32_t)cell_of(pz[j], s_box[2], inv[2]);
+            const uint32_t code = tab[cell];
+            cr[j] = (code << 16) | atomicAdd(&hist[code], 1u);
+        }
+    }
+    cluster_sync_all();                                          // #2: every slice's counters are final
+    SORT_PHASE();                 // 2: cells + histogram
+    {   // exclusive scan of the cloud's SORT_CELLS counters (sum over its slices), four consecutive cells per thread.
+        // Inside a cell the slices' points follow each other in slice order.
+        uint32_t v[4] = {0u, 0u, 0u, 0u}, lower[4] = {0u, 0u, 0u, 0u}, sum = 0;
+        for (int r = 0; r < CL; ++r) {
+            const uint4 c = (r == h) ? *reinterpret_cast<const uint4*>(hist + tid * 4) : ld_peer_u4(hist + tid * 4, (uint32_t)(cl * CL + r));
+            v[0] += c.x; v[1] += c.y; v[2] += c.z; v[3] += c.w;
+            if (r < h) { lower[0] += c.x; lower[1] += c.y; lower[2] += c.z; lower[3] += c.w; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sum += v[k];
+        uint32_t incl = sum;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t wt = warp_tot[lane], wincl = wt;                  // every warp scans the 32 warp totals itself (no second barrier)
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, wincl, d); if (lane >= d) wincl += o; }
+        const uint32_t wexcl = __shfl_sync(0xFFFFFFFFu, wincl - wt, warp);
+        uint32_t run = wexcl + incl - sum;
+        uint32_t st4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { st4[k] = run; run += v[k]; }
+        *reinterpret_cast<uint4*>(base + tid * 4) = make_uint4(st4[0] + lower[0], st4[1] + lower[1], st4[2] + lower[2], st4[3] + lower[3]);
+        if (h == 0) {   // the search kernel starts every query at the chunk of its own cell ("home" chunk)
+            uint16_t* cs = p.cellstart[cl] + (size_t)b * SORT_CELLS;
+            *reinterpret_cast<uint2*>(cs + tid * 4) = make_uint2(st4[0] | (st4[1] << 16), st4[2] | (st4[3] << 16));
+        }
+    }
+    __syncthreads();
+    SORT_PHASE();                 // 3: scan + cell starts
+    {   // every point goes to the shared memory of the CTA whose chunk slice holds its sorted position
+        const uint32_t span = (uint32_t)cps * TC_CHUNK;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nv) {
+                const uint32_t pos = base[cr[j] >> 16] + (cr[j] & 0xFFFFu);
+                const uint32_t owner = pos / span;
+                st_peer_f4(srt + (pos - owner * span), (uint32_t)(cl * CL) + owner, make_float4(px[j], py[j], pz[j], __int_as_float(i0 + k0 + j)));
+            }
+    }
+    cluster_sync_all();                                          // #3: this CTA's slice of the sorted cloud is complete
+    SORT_PHASE();                 // 4: scatter
+    // ---- this CTA's chunks: sorted rows out (one bulk copy), tile padding rows, per-chunk box / centre / radius -------------
+    float4* S = p.S[cl] + (size_t)b * nc_pad * TC_CHUNK;
+    unsigned char* Bc = p.Bc[cl] + (size_t)b * nc_pad * 32;
+    float4* box = p.box[cl] + (size_t)b * nc_pad * 2;
+    const int real_rows = max(0, min(n, c1 * TC_CHUNK) - c0 * TC_CHUNK);     // rows of this slice that hold points
+    if (tid == 0 && real_rows > 0) {
+        fence_proxy_async_smem();                                // the peers' / own generic stores -> visible to the bulk engine
+        bulk_s2g(S + (size_t)c0 * TC_CHUNK, srt, (uint32_t)real_rows * 16u);
+        bulk_commit();
+    }
+    RT();
+    float sub_sum = 0.f;
+    // a chunk = 4 consecutive lanes, lane li takes its rows li, li + 4, li + 8, li + 12 (shared-memory reads of a warp then
+    // cover whole 64-byte runs).  4 (c1 - c0) is a multiple of 32: whole warps.
+    for (int q = tid; q < 4 * (c1 - c0); q += SORT_THREADS) {
+        const int lc = q >> 2, li = q & 3, chunk = c0 + lc;
+        float x[4], y[4], z[4];
+        float l[3] = {INFINITY, INFINITY, INFINITY}, hh[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = lc * TC_CHUNK + li + 4 * j;
+            x[j] = INFINITY; y[j] = INFINITY; z[j] = INFINITY;
+            if (row < real_rows) {
+                const float4 t = srt[row];
+                x[j] = t.x; y[j] = t.y; z[j] = t.z;
+                l[0] = fminf(l[0], t.x); l[1] = fminf(l[1], t.y); l[2] = fminf(l[2], t.z);
+                hh[0] = fmaxf(hh[0], t.x); hh[1] = fmaxf(hh[1], t.y); hh[2] = fmaxf(hh[2], t.z);
+            } else {
+                S[(size_t)c0 * TC_CHUNK + row] = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0x7FFFFFFF));
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            for (int d = 2; d > 0; d >>= 1) {
+                l[a] = fminf(l[a], __shfl_xor_sync(0xFFFFFFFFu, l[a], d));
+                hh[a] = fmaxf(hh[a], __shfl_xor_sync(0xFFFFFFFFu, hh[a], d));
+            }
+        const float ccx = 0.5f * l[0] + 0.5f * hh[0], ccy = 0.5f * l[1] + 0.5f * hh[1], ccz = 0.5f * l[2] + 0.5f * hh[2];
+        float r2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (lc * TC_CHUNK + li + 4 * j < real_rows) { const float dx = x[j] - ccx, dy = y[j] - ccy, dz = z[j] - ccz; r2 = fmaxf(r2, fmaf(dz, dz, fmaf(dx, dx, dy * dy))); }
+        for (int d = 2; d > 0; d >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xFFFFFFFFu, r2, d));
+        if (li == 0 && chunk < nc) {
+            const float sub = 1.5f * r2 * sc2 * 1.001f;          // 1.5 r^2 in scaled units, inflated for the rounding of r2 itself
+            cst[lc] = make_float4(ccx, ccy, ccz, sub);
+            box[2 * chunk] = make_float4(l[0], l[1], l[2], 0.f);
+            box[2 * chunk + 1] = make_float4(hh[0], hh[1], hh[2], 0.f);
+            sub_sum += fminf(sub, 4.f);
+        }
+    }
+    RT();
+    for (int d = 16; d > 0; d >>= 1) sub_sum += __shfl_xor_sync(0xFFFFFFFFu, sub_sum, d);
+    if (lane == 0) red[0][warp] = sub_sum;                       // (a shared-memory float atomicAdd is a contended CAS loop)
+    __syncthreads();
+    RT();
+    if (warp == 0) {
+        float t = red[0][lane];
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, d);
+        if (lane == 0) s_part[7] = t;
+    }
+    cluster_sync_all();                                          // #4: every slice's radius sum is published
+    RT();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int r = 0; r < CL; ++r) t += ld_peer_f32(&s_part[7], (uint32_t)(cl * CL + r));    // same order in every CTA of the cloud
+        s_sum = t;
+    }
+    __syncthreads();
+    cluster_arrive();             // (the matching wait is the kernel's last statement: peers may still be reading s_part)
+    SORT_PHASE();                 // 5: chunk stats
+    // ---- chunk operand rows (cap and bias as in chamfer_sort_kernel) ------------------------------------------------------
+    const float cap = fminf(fmaxf(3.f * s_sum / (float)nc, 1.f / 1024.f), TC_RCAP_MAX);
+    const float e4 = 2.f * s_meta[4];                             // 4 e_tot
+    float bias = 1.f / 64.f;
+    while (bias < cap + e4 && bias < 1024.f) bias *= 2.f;
+    if (tid == 0 && h == 0) {
+        ChamferGrid gi;
+        for (int a = 0; a < 3; ++a) { gi.lo[a] = s_box[a]; gi.inv[a] = inv[a]; }
+        gi.bias = bias; gi.pad = 0.f;
+        p.grid[cl][b] = gi;
+    }
+    auto pad_chunk = [&](int c) {
+        write_b_row(Bc, c, false, 0.f, 0.f, 0.f, 0.f, 0.f);
+        box[2 * c] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
+        box[2 * c + 1] = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+    };
+    for (int c = c0 + tid; c < c1; c += SORT_THREADS) {
+        if (c < nc) {
+            const float4 ci = cst[c - c0];
+            const bool capped = !(ci.w <= cap);
+            write_b_row(Bc, c, true, (ci.x - cx) * sc, (ci.y - cy) * sc, (ci.z - cz) * sc, capped ? cap : ci.w, bias);
+            if (capped) box[2 * c].w = 1.f;
+        } else {
+            pad_chunk(c);
+        }
+    }
+    for (int c = nch + h * SORT_THREADS + tid; c < nc_pad; c += CL * SORT_THREADS) pad_chunk(c);   // whole-pass padding
+    SORT_PHASE();                 // 6: chunk rows
+#ifdef SPK_TIMING
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+        printf("sort (register) kernel phases (cycles, %d CTAs per cloud): bbox+meta %lld, cells+hist %lld, scan %lld, scatter %lld, chunk stats %lld, chunk rows %lld\n",
+               CL, tph[1] - tph[0], tph[2] - tph[1], tph[3] - tph[2], tph[4] - tph[3], tph[5] - tph[4], tph[6] - tph[5]);
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+        printf("  stats: bulk issue %lld, loop %lld, ->barrier %lld, ->csync4 %lld, ->end %lld\n", tf[0] - tph[4], tf[1] - tf[0], tf[2] - tf[1], tf[3] - tf[2], tph[5] - tf[3]);
+#endif
+    pdl_tail_trigger_bit<5>();
+    if (tid == 0) bulk_wait<0>();                                // the sorted rows' bulk copy reads this CTA's shared memory
     cluster_wait();
 }
 
@@ -965,20 +1285,44 @@ int chamfer_tc_forward(const float* xyz1, const float* xyz2, int B, int n, int m
     qp.dist[0] = dist1; qp.dist[1] = dist2; qp.idx[0] = idx1; qp.idx[1] = idx2;
 
     const int nmax = std::max(n, m);
-    size_t sort_smem = (size_t)SORT_CELLS * 4 + (size_t)((nmax + 3) & ~3) * 4 + (size_t)((nmax + 7) & ~7) * 2;
-    sp.stage = sort_smem + (size_t)nmax * 12 + 16 <= (size_t)200 * 1024;
-    if (sp.stage) sort_smem += (size_t)nmax * 12 + 16;
+    // CTAs per cloud (1, 2, 4): enough for the register kernel (a slice of at most 4 points per thread) when the clouds
+    // allow it, then as many as keep the whole grid within one wave of 1024-thread CTAs and a slice worth a CTA
+    int CL = 1;
+    while (CL < 4 && nmax > CL * SORT_THREADS * 4) CL *= 2;
+    while (CL < 4 && 2 * B * CL * 2 <= 160 && nmax / (CL * 2) >= 2048) CL *= 2;
+    if (const char* e = getenv("SPK_SORT_CTAS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) CL = v; }
+    sp.cl_ctas = CL;
+    sp.pps_max = (((nmax + CL - 1) / CL) + 3) & ~3;
+    sp.cps_max = (((int)(round_up((size_t)nmax, TC_TILE) / TC_CHUNK) + CL - 1) / CL + 7) & ~7;
+    bool reg_kernel = sp.pps_max <= SORT_THREADS * 4;
+    if (const char* e = getenv("SPK_SORT_KERNEL")) { if (strcmp(e, "generic") == 0) reg_kernel = false; }
+    const size_t sort_smem = reg_kernel ? (size_t)SORT_CELLS * 10 + (size_t)sp.cps_max * (TC_CHUNK + 1) * 16
+                                        : (size_t)SORT_CELLS * 8 + (size_t)sp.pps_max * 4 + (size_t)sp.cps_max * 16;
     // function attributes are per device; set once per (device, size) -- benign race: every writer stores the same value
     int dev = 0;
     SPK_CUDA(cudaGetDevice(&dev));
-    static size_t sort_smem_set[64] = {0};
+    static size_t sort_smem_set[64] = {0}, sort_reg_smem_set[64] = {0};
     static bool search_attr[64] = {false};
     const int dslot = (dev >= 0 && dev < 64) ? dev : 0;
-    if (sort_smem > sort_smem_set[dslot] || dev != dslot) {
+    if (!reg_kernel && (sort_smem > sort_smem_set[dslot] || dev != dslot)) {
         SPK_CUDA(cudaFuncSetAttribute(chamfer_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
         sort_smem_set[dslot] = sort_smem;
     }
-    SPK_CUDA(launch_k(chamfer_sort_kernel, dim3(2, B), dim3(SORT_THREADS), sort_smem, st, sp));
+    if (reg_kernel && (sort_smem > sort_reg_smem_set[dslot] || dev != dslot)) {
+        SPK_CUDA(cudaFuncSetAttribute(chamfer_sort_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+        sort_reg_smem_set[dslot] = sort_smem;
+    }
+    {   // one cluster per sample (2 clouds x CL CTAs), programmatic dependent launch like every kernel of the library
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * CL, B); cfg.blockDim = dim3(SORT_THREADS); cfg.dynamicSmemBytes = sort_smem; cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)(2 * CL); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        SPK_CUDA(cudaLaunchKernelEx(&cfg, reg_kernel ? chamfer_sort_reg_kernel : chamfer_sort_kernel, sp));
+    }
 
     // dynamic shared memory of at least 50 KB, so that at most 4 CTAs share an SM (each owns 128 of the 512 TMEM columns)
     // every pass's boxes + sorted points are staged in shared memory (one buffer).  The streamed variant (boxes only, points

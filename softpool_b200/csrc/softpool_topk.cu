@@ -15,6 +15,7 @@
 // Work is O(N) + O(k log^2 k) per row instead of the full O(N log^2 N) sort the reference does.
 #include "spk_common.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace spk {
 
@@ -31,10 +32,43 @@ __device__ __forceinline__ void ce_stage(uint64_t* buf, int len, int size, int s
     }
 }
 
-// Strides <= 32 only move data inside the 64-element block a warp-iteration owns, so those
-// stages need a __syncwarp only; a CTA barrier is needed around every stride >= 64 stage.
-__device__ __forceinline__ void stage_sync(int stride, int prev_stride) {
-    if (stride >= 64 || prev_stride >= 64) __syncthreads(); else __syncwarp();
+// Strides < 32 * EPL only move data inside an aligned block of 32 * EPL elements.  A warp takes such a block into registers
+// (lane l holds elements l, l + 32, ...), runs every consecutive stage with such a stride there -- strides >= 32 between its
+// own registers, smaller ones by shuffle -- and writes it back once: the stages that sort a block and the last stages of
+// every later merge cost one shared-memory round trip each instead of one per stage (55 -> 10 block-wide steps at 1024
+// survivors with 128-element blocks).
+template <int EPL>
+__device__ __forceinline__ void block_stages(uint64_t* buf, int base, int lane, int size_lo, int size_hi) {
+    uint64_t e[EPL];
+#pragma unroll
+    for (int u = 0; u < EPL; ++u) e[u] = buf[base + lane + 32 * u];
+    for (int size = size_lo; size <= size_hi; size <<= 1) {
+        bool desc[EPL];
+#pragma unroll
+        for (int u = 0; u < EPL; ++u) desc[u] = ((base + lane + 32 * u) & size) == 0;
+#pragma unroll
+        for (int rs = EPL / 2; rs > 0; rs >>= 1) {         // stride 32 * rs: between the lane's own registers
+            if (size >= 64 * rs) {
+#pragma unroll
+                for (int u = 0; u < EPL; ++u)
+                    if ((u & rs) == 0) {                   // (desc[u] == desc[u + rs]: size > stride)
+                        const bool sw = (e[u] < e[u + rs]) == desc[u];
+                        const uint64_t a = sw ? e[u + rs] : e[u], c = sw ? e[u] : e[u + rs];
+                        e[u] = a; e[u + rs] = c;
+                    }
+            }
+        }
+        for (int stride = min(size >> 1, 16); stride > 0; stride >>= 1) {
+            const bool lower = (lane & stride) == 0;       // this lane keeps the first of the pair
+#pragma unroll
+            for (int u = 0; u < EPL; ++u) {
+                const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, e[u], stride);
+                e[u] = (lower == desc[u]) ? (o > e[u] ? o : e[u]) : (o < e[u] ? o : e[u]);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < EPL; ++u) buf[base + lane + 32 * u] = e[u];
 }
 
 // exclusive prefix sum of one int per thread over the NT-thread CTA; returns the grand total
@@ -61,7 +95,10 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot /*[NT/3
     return base + inc - v;
 }
 
-template <int NT>
+// AMV: the Sorter arg-max reads four consecutive points per thread and row with 128-bit loads and the row's keys arrive
+// eight float4 at a time (long rows, whose slices keep every thread busy: N / R >= 4 NT); otherwise one point per thread
+// and four float4 at a time, which keeps the kernel at 40 registers for the short rows.
+template <int NT, bool AMV>
 __global__ void __launch_bounds__(NT)
 sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K2, int KS, int vec_ok,
                int32_t* __restrict__ idx, float* __restrict__ sp_idx,
@@ -87,31 +124,39 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
 #define TQ(i)
 #endif
 
-    // ---- arg-max operands first: this thread's first point of the slice, up to 8 of the R rows, straight into
+    // ---- arg-max operands first: this thread's first points of the slice, up to 8 of the R rows, straight into
     // registers -- issued BEFORE the row's own loads, so that both batches share one trip to L2 / DRAM instead
-    // of queueing behind each other (the arg-max itself is formed after the keys are parked)
+    // of queueing behind each other (the arg-max itself is formed after the keys are parked).  Aligned rows: four
+    // consecutive points per thread and row (one 128-bit load each); otherwise one point per thread.
     constexpr int AM_PRE = 8;
-    float am[AM_PRE];
+    typename std::conditional<AMV, float4, float>::type am[AM_PRE];
     const int am_slice = (N + R - 1) / R;
     const int am_s0 = r * am_slice, am_s1 = min(N, am_s0 + am_slice);
     const float* kb = keys + (size_t)b * R * N;
-    const bool am_mine = id_activa != nullptr && am_s0 + tid < am_s1;
+    const bool am_mine = id_activa != nullptr && (AMV ? am_s0 + 4 * tid < am_s1 : am_s0 + tid < am_s1);
+    if constexpr (AMV) {
 #pragma unroll
-    for (int rr = 0; rr < AM_PRE; ++rr) am[rr] = (am_mine && rr < R) ? __ldg(kb + (size_t)rr * N + am_s0 + tid) : 0.f;
+        for (int rr = 0; rr < AM_PRE; ++rr)
+            am[rr] = (am_mine && rr < R) ? __ldg(reinterpret_cast<const float4*>(kb + (size_t)rr * N + am_s0 + 4 * tid)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+        for (int rr = 0; rr < AM_PRE; ++rr) am[rr] = (am_mine && rr < R) ? __ldg(kb + (size_t)rr * N + am_s0 + tid) : 0.f;
+    }
 
     // ---- 1. load: thread t owns the E consecutive points n = t*E .. t*E+E-1 ------------------------
     // (all loads are issued before the first use: order_key is branch-free, nothing serialises them)
     const int n0 = tid * E;
     if (vec_ok && (E & 3) == 0 && (N & 3) == 0) {
-        for (int e0 = 0; e0 < E; e0 += 16) {
-            float4 v[4];
+        constexpr int LW = AMV ? 8 : 4;                             // float4 loads in flight per thread
+        for (int e0 = 0; e0 < E; e0 += 4 * LW) {
+            float4 v[LW];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < LW; ++u) {
                 const int n = n0 + e0 + 4 * u;
                 v[u] = (e0 + 4 * u < E && n < N) ? __ldg(reinterpret_cast<const float4*>(krow + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < LW; ++u) {
                 const int e = e0 + 4 * u;
                 if (e < E) {
                     const bool in = n0 + e < N;                             // N%4==0: all four or none
@@ -137,7 +182,31 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     if (tid == 0) cand_cnt = 0;
 
     // ---- argmax over the R rows for this CTA's slice of n (softpool.py:95) --------------------------
-    if (id_activa != nullptr) {
+    if constexpr (AMV) {
+        if (id_activa != nullptr) {
+            for (int n = am_s0 + 4 * tid, first = 1; n < am_s1; n += 4 * NT, first = 0) {
+                if (!first) {
+#pragma unroll
+                    for (int rr = 0; rr < AM_PRE; ++rr)
+                        if (rr < R) am[rr] = __ldg(reinterpret_cast<const float4*>(kb + (size_t)rr * N + n));
+                }
+                uint32_t bk[4] = {order_key(am[0].x), order_key(am[0].y), order_key(am[0].z), order_key(am[0].w)};
+                int bi[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int rr = 1; rr < AM_PRE; ++rr) {
+                    const uint32_t kk[4] = {order_key(am[rr].x), order_key(am[rr].y), order_key(am[rr].z), order_key(am[rr].w)};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool better = rr < R && kk[u] > bk[u];     // strict: first maximum / first NaN
+                        bk[u] = better ? kk[u] : bk[u]; bi[u] = better ? rr : bi[u];
+                    }
+                }
+                longlong2* o = reinterpret_cast<longlong2*>(id_activa + (size_t)b * N + n);
+                o[0] = make_longlong2((long long)bi[0], (long long)bi[1]);
+                o[1] = make_longlong2((long long)bi[2], (long long)bi[3]);
+            }
+        }
+    } else if (id_activa != nullptr) {
         const int s0 = am_s0, s1 = am_s1;
         if (am_mine) {                                           // first point: the first AM_PRE rows are in registers
             uint32_t bestk = order_key(am[0]);
@@ -175,6 +244,9 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     // above it: the k-th largest key is >= T0.  Everything >= T0 (about 2 k keys; all ties of the k-th key included) is
     // compacted in index order and sorted; the first k words are the stable descending prefix.  Falls through to the radix
     // select when more than KS keys survive (heavy ties).
+    // (For larger k the same shortcut with a sampled pivot -- an order statistic of NT keys, aimed at 1.5 k survivors, ordered
+    // by a bucket / rank sort or a bitonic network over 2 K2 slots -- was built and measured: 36 us at N = 8192, k = 1024 against
+    // ~30 us for the radix select below followed by the fused network over K2 slots; dropped, profiles/README.md.)
     int K2s = K2;                                        // slots the survivor sort works on
     bool done_fast = false;
 #ifndef SPK_NO_TOPK_SHORTCUT
@@ -328,13 +400,22 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
             if (lane < K2s) sel[lane] = v;
         }
     } else {
-        int prev = 64;
-        for (int size = 2; size <= K2s; size <<= 1)
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                stage_sync(stride, prev);
-                ce_stage(sel, K2s, size, stride, tid, NT);
-                prev = stride;
+        // K2s is a power of two >= 64.  Blocks of 128 words when that still gives every warp one (K2s >= 1024), else of 64:
+        // measured at K2s = 256, sort phase 3.9k cycles with 64-word blocks (4 warps busy) against 7.5k with 128-word ones
+        __syncthreads();
+        auto fused_sort = [&](auto epl_tag) {
+            constexpr int EPL = decltype(epl_tag)::value, BL = 32 * EPL;
+            for (int base = warp * BL; base < K2s; base += (NT / 32) * BL) block_stages<EPL>(sel, base, lane, 2, BL);
+            for (int size = 2 * BL; size <= K2s; size <<= 1) {
+                for (int stride = size >> 1; stride >= BL; stride >>= 1) {
+                    __syncthreads();
+                    ce_stage(sel, K2s, size, stride, tid, NT);
+                }
+                __syncthreads();
+                for (int base = warp * BL; base < K2s; base += (NT / 32) * BL) block_stages<EPL>(sel, base, lane, size, size);
             }
+        };
+        if (K2s >= 1024) fused_sort(std::integral_constant<int, 4>()); else fused_sort(std::integral_constant<int, 2>());
     }
     __syncthreads();
     TQ(4);
@@ -342,12 +423,15 @@ sp_topk_kernel(const float* __restrict__ keys, int R, int N, int k, int E, int K
     // ---- emit ---------------------------------------------------------------------------------------------
     pdl_tail_trigger();
     int32_t* orow = idx + (size_t)row * k;
-    for (int j = tid; j < k; j += NT) orow[j] = (int32_t)(0xFFFFFFFFu - (uint32_t)sel[j]);
-    if (sp_idx != nullptr) {
-        const int Q = R + 3;
-        for (int e = tid; e < Q * k; e += NT) {
-            const int q = e / k, j = e - q * k;
-            sp_idx[(((size_t)b * Q + q) * R + r) * k + j] = (float)(0xFFFFFFFFu - (uint32_t)sel[j]);
+    {   // one shared-memory read per survivor, then its R + 3 float copies (softpool.py:136-137,146-147), coalesced per copy
+        const int Q = sp_idx != nullptr ? R + 3 : 0;
+        float* cube = sp_idx != nullptr ? sp_idx + ((size_t)b * (R + 3) * R + r) * k : nullptr;
+        const size_t qstride = (size_t)R * k;
+        for (int j = tid; j < k; j += NT) {
+            const uint32_t n = 0xFFFFFFFFu - (uint32_t)sel[j];
+            orow[j] = (int32_t)n;
+            const float fv = (float)n;
+            for (int q = 0; q < Q; ++q) cube[(size_t)q * qstride + j] = fv;
         }
     }
 #ifdef SPK_TIMING
@@ -406,7 +490,11 @@ extern "C" int sp_topk_f32(const float* keys, int B, int R, int N, int k, int32_
         SPK_CUDA(launch_k(kern, dim3(B * R), dim3(NT), smem, (cudaStream_t)stream, keys, R, N, k, E, K2, KS, vec_ok, idx, sp_idx, id_activa));
         return SPK_OK;
     };
-    return NT == 1024 ? launch(sp_topk_kernel<1024>) : NT == 512 ? launch(sp_topk_kernel<512>) : NT == 128 ? launch(sp_topk_kernel<128>) : launch(sp_topk_kernel<256>);
+    // wide loads (AMV) for rows whose arg-max slices keep every thread busy with four points; needs aligned rows
+    const int am_slice = (N + R - 1) / R;
+    const bool amv = vec_ok && (N & 3) == 0 && (am_slice & 3) == 0 && am_slice >= 4 * NT && R <= 8 && (!id_activa || ((uintptr_t)id_activa & 15) == 0);
+    if (amv) return NT == 1024 ? launch(sp_topk_kernel<1024, true>) : NT == 512 ? launch(sp_topk_kernel<512, true>) : NT == 128 ? launch(sp_topk_kernel<128, true>) : launch(sp_topk_kernel<256, true>);
+    return NT == 1024 ? launch(sp_topk_kernel<1024, false>) : NT == 512 ? launch(sp_topk_kernel<512, false>) : NT == 128 ? launch(sp_topk_kernel<128, false>) : launch(sp_topk_kernel<256, false>);
 }
 
 extern "C" int sp_argmax_i64(const float* keys, int B, int R, int N, int64_t* id_activa, void* stream) {

@@ -141,6 +141,30 @@ __device__ __forceinline__ void bulk_wait() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- thread-block clusters: barrier (release / acquire at cluster scope) and distributed shared memory ----------
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+__device__ __forceinline__ float ld_peer_f32(const float* own_smem, uint32_t peer_rank) {
+    uint32_t ra; float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(own_smem)), "r"(peer_rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ uint4 ld_peer_u4(const uint32_t* own_smem, uint32_t peer_rank) {
+    uint32_t ra; uint4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(own_smem)), "r"(peer_rank));
+    asm volatile("ld.shared::cluster.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ra) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_peer_f4(const float4* own_smem, uint32_t peer_rank, float4 v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(own_smem)), "r"(peer_rank));
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // ---- programmatic dependent launch (PDL): the next kernel of the stream may start its prologue while this
 // one drains; pdl_wait() blocks until the previous kernel has completed and its writes are visible.
 __device__ __forceinline__ void pdl_trigger() {

@@ -347,6 +347,24 @@ def test_split_jobs_are_bit_identical(split, monkeypatch):
         assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
 
 
+@pytest.mark.parametrize("kernel,ctas", [("auto", 1), ("auto", 2), ("auto", 4), ("generic", 1), ("generic", 2), ("generic", 4)])
+@pytest.mark.parametrize("B,n,m", [(2, 3001, 5000), (1, 700, 16384), (3, 4097, 4096)])
+def test_sort_kernels_and_cluster_sizes_are_bit_identical(kernel, ctas, B, n, m, monkeypatch):
+    """The sorted search's prep step runs as a cluster of 2 x {1, 2, 4} CTAs per sample, in a register form (slices of up to
+    4096 points) or the generic form: whichever sorts the clouds, dist / idx are the oracle's bit for bit (ragged sizes,
+    slices that end inside a chunk, an empty last slice, duplicates that land in different slices)."""
+    a, b = clouds(B, n, m, seed=ctas + n)
+    b[:, m - 100:] = b[:, 100:200]
+    r = co.forward(a, b)
+    monkeypatch.setenv("SPK_CHAMFER_PATH", "sorted")
+    monkeypatch.setenv("SPK_SORT_CTAS", str(ctas))
+    if kernel != "auto":
+        monkeypatch.setenv("SPK_SORT_KERNEL", kernel)
+    o = cuda_forward(a, b)
+    for x, y in zip(o, r):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
 def test_cluster_backward_matches_two_kernel_form(monkeypatch):
     """One cluster launch per call (default) against the two-launch form (pass A, pass B), on a size whose
     points exceed what a cluster's threads hold in registers, and against the oracle."""
