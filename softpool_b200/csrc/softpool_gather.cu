@@ -902,15 +902,16 @@ static int gather_bwd_pull(const float* g_cube, const float* g_cabins, const int
     // the window-max gradient rides along as bulk copies when every group's byte ranges are 16-byte multiples
     p.cab_bulk = g_cabins != nullptr && (wins % 8) == 0 && (((uintptr_t)g_cabins & 15) == 0) && (((uintptr_t)cab_arg & 15) == 0);
     if (tune_env("SPK_PULL_NOCABBULK")) p.cab_bulk = 0;
-    // T rows per group: as many as keep three CTAs per SM; tables / tiles too large for that: up to two
-    // rows in one wide CTA per SM
-    int T = 8;
+    // T rows per group, by the size of a gradient row (measured, us per call at T / threads; B=32, C=256, R=8, k=N/8):
+    //   R*k =  256 (N=2048, k=32): 8/128 14.2 (a deeper ring or wider CTAs are slower)
+    //   R*k = 1024 (N=1024):       8/128 26.0, 4/128 23.3
+    //   R*k = 2048 (N=2048):       2/128 39.8, 4/128 47.2, 4/256 37.9, 8/256 51.0
+    //   R*k = 4096 (N=4096):       1/128 83.5, 2/128 88.1, 2/256 67.9, 4/512 69.8
+    //   R*k = 8192 (N=8192):       2/512 140.9, 2/256 156.7, 3/512 150.6
+    // i.e. a tile of 16-32 KB, and (below) the CTA width that keeps >= 16 warps on an SM for the CTAs that fit
+    int T = RK <= 512 ? 8 : RK <= 2048 ? 4 : 2;
     if (const char* e = tune_env("SPK_PULL_T")) { T = atoi(e); if (T != 1 && T != 2 && T != 4 && T != 8) return fail(SPK_E_BADARG, "SPK_PULL_T must be 1, 2, 4 or 8"); }
-    else {
-        while (T > 1 && fixed + 2 * pull_slot_bytes(T, (int)RK, wins, p.cab_bulk) > target) T >>= 1;
-        if (T == 1 && fixed + 2 * pull_slot_bytes(1, (int)RK, wins, p.cab_bulk) > target &&
-            fixed + 2 * pull_slot_bytes(2, (int)RK, wins, p.cab_bulk) <= budget) T = 2;
-    }
+    while (T > 1 && fixed + 2 * pull_slot_bytes(T, (int)RK, wins, p.cab_bulk) > budget) T >>= 1;
     T = std::max(1, std::min(8, T));
     while (T > 1 && T / 2 >= C) T >>= 1;
     const size_t tile = pull_slot_bytes(T, (int)RK, wins, p.cab_bulk);
@@ -928,8 +929,8 @@ static int gather_bwd_pull(const float* g_cube, const float* g_cabins, const int
     // CTA width: narrow CTAs (128 threads) put more independent CTAs on an SM, so one CTA's table build /
     // tile wait / fold overlaps another's stores (measured at config A: 14.0 us vs 18.6 us with 256);
     // with at most two resident CTAs (large tables / tiles) 512 threads keep enough warps per SM
-    int threads = 128;
-    if (T < 8 && (228 * 1024) / (smem + 1024) <= 2) threads = 512;
+    const int resident = (int)((228 * 1024) / (smem + 1024));
+    int threads = resident <= 1 ? 512 : resident <= 3 ? 256 : 128;
     if (const char* e = tune_env("SPK_PULL_THREADS")) threads = atoi(e);
     if (T == 8 && threads > 256) threads = 256;
 #define SPK_PULL_CASE(TT)                                                            \
