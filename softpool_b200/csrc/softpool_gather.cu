@@ -65,6 +65,7 @@ struct GatherFwdParams {
     int vec4;             // k%4==0 && sp_cube 16B aligned: 4 slots per work item, 128-bit stores
     int cab_fast;         // windows are whole groups of 4 slots, (wl/4) pow2 <= 32, (R*k/4) % 32 == 0 if > 1
     int g_shift;          // log2(wl/4) when cab_fast
+    int cab_wide;         // windows of exactly 256 slots (k/cab == 256, e.g. N = 16384, k = 2048): a work item = 8 slots, a window = one warp
     int q_shift;          // log2(R*k/4) when that is a power of two, else -1
     int q_cols;           // dense case: R*k/4 is a multiple of the CTA width -> a thread keeps its 4-slot groups for all rows of a tile
 };
@@ -170,6 +171,38 @@ sp_gather_fwd_kernel(const GatherFwdParams p) {
                             p.cab_arg[cab_o] = (uint16_t)woff;
                         }
                     }
+                }
+            }
+        } else if (p.cab_wide) {
+            // 256-slot windows: an item = 8 consecutive slots (two 128-bit stores), the 32 lanes of a warp = one window; the
+            // window max is two warp reductions as above.  (Without this the window max ran as a second kernel that re-read
+            // sp_cube: N = 16384 forward 328 us.)
+            const int Q8 = RK >> 3;                                                   // items per row (a multiple of 32)
+            const int items = rows * Q8;                                              // whole warps: live is warp-uniform
+            for (int e = tid; e < items; e += G_THREADS) {
+                const int t = e / Q8, q8 = e - t * Q8;
+                const float* row = tile + (size_t)t * N;
+                const uint4 u = *reinterpret_cast<const uint4*>(idx_s + 8 * q8);
+                float v[8];
+                v[0] = row[u.x & 0xFFFFu]; v[1] = row[u.x >> 16]; v[2] = row[u.y & 0xFFFFu]; v[3] = row[u.y >> 16];
+                v[4] = row[u.z & 0xFFFFu]; v[5] = row[u.z >> 16]; v[6] = row[u.w & 0xFFFFu]; v[7] = row[u.w >> 16];
+                float4* outp = reinterpret_cast<float4*>(p.sp_cube + (size_t)(g + t) * RK) + 2 * q8;
+                st_cs_f4(outp, make_float4(v[0], v[1], v[2], v[3]));
+                st_cs_f4(outp + 1, make_float4(v[4], v[5], v[6], v[7]));
+                // torch.max over the window: first maximum, a NaN wins (first NaN); -0 == +0
+                float best = v[0]; uint32_t off = 0;
+#pragma unroll
+                for (int j = 1; j < 8; ++j)
+                    if (!(v[j] <= best) && best == best) { best = v[j]; off = (uint32_t)j; }
+                uint32_t woff = off + ((uint32_t)(q8 & 31) << 3);
+                const uint32_t key = order_key(best);
+                const uint32_t kmax = __reduce_max_sync(0xFFFFFFFFu, key);
+                woff = __reduce_min_sync(0xFFFFFFFFu, key == kmax ? woff : 0xFFFFFFFFu);
+                if ((q8 & 31) == 0) {
+                    const int win = q8 >> 5;                                          // (r, w) flattened
+                    const size_t o = (size_t)(g + t) * wins_per_row + win;
+                    p.cabins[o] = row[idx_s[win * wl + (int)woff]];                   // the value itself comes from the winning slot
+                    p.cab_arg[o] = (uint16_t)woff;
                 }
             }
         } else if (p.vec4) {
@@ -786,6 +819,7 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
     p.cab_fast = want_cab && p.vec4 && (k % cab == 0) && (wl % 4 == 0) && G <= 32 && ilog2_exact(G) >= 0 &&
                  (G == 1 || ((RK >> 2) % 32) == 0);
     p.g_shift = p.cab_fast ? ilog2_exact(G) : 0;
+    p.cab_wide = want_cab && !p.cab_fast && p.vec4 && (k % cab == 0) && wl == 256 && ((RK >> 3) % 32) == 0;
     p.q_shift = ilog2_exact((int)(RK >> 2));
     // tile size / CTA width: 256 threads with two ~32 KB tiles (3 CTAs per SM), or -- SPK_FWD_THREADS=128 --
     // narrow CTAs with two ~16 KB tiles (6 CTAs per SM)
@@ -803,6 +837,7 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
     else if (fixed + 2 * (size_t)T * row_bytes > (size_t)72 * 1024 && !tune_env("SPK_FWD_THREADS")) threads = 512;   // two CTAs per SM: 32 warps
     // the per-group hoisting only pays when a tile holds several rows (measured: N=2048 33 vs 34.5 us; one row per tile, N=8192: 169 vs 145 us)
     p.q_cols = T >= 2 && p.vec4 && ((RK >> 2) % threads) == 0 && (!want_cab || p.cab_fast) && !tune_env("SPK_FWD_NO_QCOLS");
+    if (p.q_cols) p.cab_wide = 0;
     const size_t smem = fixed + 2 * (size_t)T * row_bytes;
     auto launch = [&](auto kern, int nt) -> int {
         if (smem > 48 * 1024)
@@ -815,7 +850,7 @@ extern "C" int sp_gather_fwd_f32(const float* x, const int32_t* idx, int B, int 
     const int rc = threads == 128 ? launch(sp_gather_fwd_kernel<128>, 128) : threads == 1024 ? launch(sp_gather_fwd_kernel<1024>, 1024) :
                    threads == 512 ? launch(sp_gather_fwd_kernel<512>, 512) : launch(sp_gather_fwd_kernel<256>, 256);
     if (rc != SPK_OK) return rc;
-    if (want_cab && !p.cab_fast) {
+    if (want_cab && !p.cab_fast && !p.cab_wide) {
         const long long n_rows = (long long)B * C * R;
         const long long total = n_rows * cab;
         const long long work = (k / cab >= 32) ? total * 32 : total;            // a warp per long window

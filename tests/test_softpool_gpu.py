@@ -78,6 +78,7 @@ SEEDED = [
     (2, 8, 3000, 4, 750, 10),
     (1, 256, 2048, 8, 32, 8),        # full C of config 2
     (1, 512, 2048, 8, 256, 8),       # C sweep top end
+    (2, 6, 4096, 4, 1024, 4),        # 256-slot windows, two rows per tile (the fused wide window max)
 ]
 
 
