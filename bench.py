@@ -546,19 +546,27 @@ def run_e2e(args, w, dev, stream, spd):
             free[j].record(stream)
         run(3)
         stream.synchronize(); copy_stream.synchronize(); back_stream.synchronize()
-        spd.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        copy_stream.wait_event(e0)                       # no copy of the timed steps starts before the clock does
-        back_stream.wait_event(e0)
-        for j in range(2):
-            free[j].record(stream)
-        run(steps)
-        e1.record(stream)                                # after the last step's kernels AND its D2H copies (stream waited for `copied`)
-        stream.synchronize(); copy_stream.synchronize(); back_stream.synchronize()
-    ms = spd.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+        # the timed region, three times over: host memory / PCIe are shared with whatever else runs on the box, and one
+        # disturbed window of ~50 ms (seen: 26.9 and 2.9 Mpoints/s on a box that gave 35 a minute earlier) would otherwise be
+        # the reported number.  Every repetition is a complete measurement (barrier, max over ranks); the best one is reported,
+        # all three are listed -- the reference arm is a best-of-3 as well.
+        runs = []
+        for rep in range(3):
+            spd.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            copy_stream.wait_event(e0)                   # no copy of the timed steps starts before the clock does
+            back_stream.wait_event(e0)
+            for j in range(2):
+                free[j].record(stream)
+            run(steps)
+            e1.record(stream)                            # after the last step's kernels AND its D2H copies (stream waited for `copied`)
+            stream.synchronize(); copy_stream.synchronize(); back_stream.synchronize()
+            runs.append(spd.max_over_ranks(e0.elapsed_time(e1), dev) / steps)
+    ms = min(runs)
     pts = spd.sum_over_ranks(B * N, dev)
     return {"value": pts / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "ms_per_step_runs": [round(r, 4) for r in runs], "reported": "best of 3 timed regions of `steps` steps each",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "d2h": "every output: " + ", ".join(outs),
             "api": "ops.softpool_topk + ops.softpool_gather (autograd) + chamferDist (autograd); pinned host tensors, "
