@@ -2,16 +2,18 @@
 //
 // Replaces the region loop's `torch.sort(..., descending=True)` + `[:, :k]` (reference
 // softpool.py:139-142), the float index cube (softpool.py:136-137,146-147) and the Sorter's
-// argmax (softpool.py:95).  One 256-thread CTA per (b, r) row, 8 CTAs per SM.
+// argmax (softpool.py:95).  One CTA per (b, r) row (256 threads; 512 above N = 8192).
 //
 // Algorithm (select, compact, sort the survivors):
 //   1. keys -> order_key (u32 total order: NaN first, -0 == +0), parked in shared memory;
-//   2. radix select, 2 bits per round (16 rounds, one barrier each): the largest V with
-//      #(key >= V) >= k is the k-th largest key;
+//   2. k <= 32: a threshold T0 from warp maxima with >= k keys at or above it, everything >= T0 survives;
+//      otherwise radix select, 4 bits per round (<= 8 rounds, one barrier each, early finish when the chosen
+//      bucket holds <= 32 keys): the largest V with #(key >= V) >= k is the k-th largest key;
 //   3. everything > V is selected, plus the first k - #(key > V) of the keys == V in ascending
 //      index order (block prefix sums) -> the selected SET equals the stable-sort prefix;
-//   4. the k survivors, packed as unique u64 (key << 32 | ~n), are bitonic-sorted descending:
-//      ties come out in ascending n, i.e. the stable descending order of the reference.
+//   4. the survivors, packed as unique u64 (key << 32 | ~n), are bitonic-sorted descending (stages inside a 64- or
+//      128-word block run in registers / shuffles): ties come out in ascending n, i.e. the stable descending
+//      order of the reference.
 // Work is O(N) + O(k log^2 k) per row instead of the full O(N log^2 N) sort the reference does.
 #include "spk_common.cuh"
 #include <stdlib.h>
