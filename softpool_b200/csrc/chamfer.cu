@@ -396,10 +396,16 @@ extern "C" int chamfer_bwd_f32(const float* xyz1, const float* xyz2, const float
     const long long t1 = (long long)B * n, t2 = (long long)B * m;
     const char* two = getenv("SPK_CH_BWD_TWO_KERNELS");
     if (!(two && two[0] == '1') && (long long)n + m < (1LL << 30)) {
-        // one cluster per sample, sized so that a thread holds <= CHB_PPT points when 8 CTAs suffice
+        // one cluster per sample, sized so that a thread holds <= CHB_PPT points when 8 CTAs suffice, then widened until the
+        // grid covers the machine as long as every thread keeps a point: the kernel is two dependent latency chains, more
+        // CTAs shorten both (B=32, 2048<->2048: 2 CTAs per sample 7.4 us, 4 or 8: 5.3 us)
         const long long per_cta = (long long)CHB_THREADS * CHB_PPT;
         int cl = 1;
         while (cl < 8 && (long long)cl * per_cta < (long long)n + m) cl <<= 1;
+        while (cl < 8 && (long long)B * cl < 128 && 2LL * cl * CHB_THREADS <= (long long)n + m) cl <<= 1;
+#ifdef SPK_EXPERIMENT
+        if (const char* e = getenv("SPK_CH_BWD_CL")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) cl = v; }
+#endif
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(B * cl)); cfg.blockDim = dim3(CHB_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
         cudaLaunchAttribute at[2];
